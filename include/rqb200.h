@@ -1,0 +1,124 @@
+/* librqb200 -- C ABI of the B200-native RQ-VAE residual-quantisation hot path.
+ *
+ * The reference (EdoardoBotta/RQ-VAE-Recommender) has no FFI layer: its boundary is the Python module API
+ * (modules/quantize.py, modules/rqvae.py, init/kmeans.py, distributions/gumbel.py, modules/encoder.py).
+ * This header is the C boundary those replacement modules bind (via ctypes, see
+ * rq_vae_recommender_b200/_lib.py and INTEGRATION.md).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host (`const float* const* codebooks` is a HOST
+ *     array of L device pointers); row-major storage; strides/leading dimensions are in ELEMENTS;
+ *   - no allocation, no ownership transfer: the caller (PyTorch) allocates outputs and workspaces
+ *     (sizes from the *_workspace_bytes queries) and keeps them alive until the stream work completes;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises the host;
+ *   - every function returns 0 on success or an RQB_ERR_* code; rqb200_last_error() gives the text
+ *     (thread-local).  No exceptions cross the boundary.  No global mutable state besides that string.
+ */
+#ifndef RQB200_H
+#define RQB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RQB_OK 0
+#define RQB_ERR_INVALID 1
+#define RQB_ERR_CUDA 2
+#define RQB_ERR_UNSUPPORTED 3
+#define RQB_ERR_WORKSPACE 4
+
+#define RQB_MAX_LEVELS 8
+
+/* forward modes: numbering of modules/quantize.py:16-20 (QuantizeForwardMode), 0 = eval-mode lookup */
+#define RQB_MODE_EVAL 0
+#define RQB_MODE_GUMBEL 1
+#define RQB_MODE_STE 2
+#define RQB_MODE_ROTATION 3
+
+int rqb200_version(void);
+const char* rqb200_last_error(void);
+int rqb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- fused L-level residual quantisation, exact fp32 -------------------------------------------------
+ * Replaces L x Quantize.forward (modules/quantize.py:104-163: distance :113-117, argmin :128, eval lookup
+ * :159-161, STE :137-139, rotation trick :140-153 + :34-50, QuantizeLoss modules/loss.py:38-41) chained by
+ * RqVae.get_semantic_ids (modules/rqvae.py:122-139: residual update :130, loss accumulation :128).
+ * x is the encoder output [B,D] (ldx >= D).  All outputs are optional (NULL = not produced):
+ *   ids [B,L] int64; embeddings / residuals [L,B,D] (the Python side returns [B,D,L] views);
+ *   emb_sum [B,D] = sum_l emb_out (rqvae.py:146); emb_norms [B,L] = ||emb_out|| (rqvae.py:158); loss [B].
+ * Tokenisation (modules/tokenizer/semids.py:125) is mode = EVAL with only `ids`. */
+size_t rqb200_rq_workspace_bytes(int D, int K, int L);
+int rqb200_rq_forward(int mode, const float* x, int64_t ldx, const float* const* codebooks, int B, int D, int K,
+                      int L, float beta, int64_t* ids, float* embeddings, float* residuals, float* emb_sum,
+                      float* emb_norms, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above (autograd of quantize.py:130-161 + loss.py:38-41 through the chain rqvae.py:125-132;
+ * formulas SURVEY appendix A.3).  Upstream grads come with element strides so expanded / permuted torch
+ * tensors need no copy: g_emb[b,d,l] = g_emb[b*ge_sB + d*ge_sD + l*ge_sL] (NULL = zero), same for g_res;
+ * g_loss[b*gl_sB].  g_x [B,D] is written; g_codebooks[l] [K,D] are ACCUMULATED (caller zero-fills). */
+int rqb200_rq_backward(int mode, const float* x, int64_t ldx, const float* const* codebooks, const int64_t* ids,
+                       int B, int D, int K, int L, float beta, const float* g_emb, int64_t ge_sB, int64_t ge_sD,
+                       int64_t ge_sL, const float* g_res, int64_t gr_sB, int64_t gr_sD, int64_t gr_sL,
+                       const float* g_loss, int64_t gl_sB, float* g_x, float* const* g_codebooks, void* stream);
+
+/* ---- tensor-core tokeniser (tcgen05 candidate filter + exact fp32 re-rank), see csrc/rq_tc.cu --------
+ * Same result contract as rqb200_rq_forward(mode=EVAL, ids only).  `prepare` converts the codebooks once
+ * (fp16 copies, norms, inter-level Gram tables) into `state`; `run` consumes x [B,D] fp32. */
+size_t rqb200_tokenize_tc_state_bytes(int D, int K, int L);
+int rqb200_tokenize_tc_supported(int D, int K, int L);
+int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, int K, int L, void* state, size_t state_bytes,
+                               void* stream);
+int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const void* state, int D, int K, int L,
+                           int64_t* ids, int* stats, void* stream);
+
+/* ---- k-means codebook initialisation (init/kmeans.py) ------------------------------------------------
+ * assign_accumulate = one Lloyd assignment pass with the direct (x-c)^2 distance of kmeans.py:40-43 plus the
+ * per-cluster sums (fp64) and counts that kmeans.py:48-58 derives with a Python loop; in the sharded setting
+ * the caller all-reduces sums/counts between the two calls.  finalize writes the new centroids in place
+ * (mean, or x[reseed_rows[k]] for an empty cluster, kmeans.py:50-54; reseed_rows may be NULL) and the
+ * max centroid shift of kmeans.py:68 into *max_shift (device float). */
+int rqb200_kmeans_assign_accumulate(const float* x, int64_t ldx, const float* centroids, int B, int D, int K,
+                                    int64_t* assignment, double* sums, int* counts, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+int rqb200_kmeans_finalize(const double* sums, const int* counts, const float* x, int64_t ldx,
+                           const int64_t* reseed_rows, float* centroids, int K, int D, float* max_shift,
+                           void* stream);
+
+/* ---- dense fp32 helpers -------------------------------------------------------------------------------
+ * sgemm: C = epi(alpha * op(A) op(B) + beta * C), row-major, op = transpose flag; relu and the (mask > 0)
+ * epilogue fuse the ReLU forward / backward of modules/encoder.py:27-29.  Also the W@C and gradient GEMMs of
+ * the Gumbel path (quantize.py:135). */
+int rqb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                 const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int relu, const float* mask,
+                 int64_t ldmask, void* stream);
+int rqb200_row_sqnorm(const float* c, int K, int D, float* out, void* stream);
+/* dots [B,K] (= x @ C^T) -> dist in place (quantize.py:113-117) + first-index argmin (quantize.py:128) */
+int rqb200_dist_finish(float* dots, const float* x, int64_t ldx, const float* cc, int B, int D, int K, int64_t* ids,
+                       void* stream);
+/* W = softmax((-dist + G(U)) / T)  (distributions/gumbel.py:8-20 with U injected; quantize.py:132-134) */
+int rqb200_gumbel_softmax_fwd(const float* dist, const float* uniform, float* weights, int B, int K,
+                              float temperature, void* stream);
+int rqb200_gumbel_row_finish(const float* x, int64_t ldx, const float* E, int B, int D, float beta, float* loss,
+                             void* stream);
+int rqb200_gumbel_bwd_ge(const float* g_out, int64_t go_sB, int64_t go_sD, const float* g_loss, int64_t gl_sB,
+                         const float* x, int64_t ldx, const float* E, float* gE, int B, int D, void* stream);
+int rqb200_gumbel_bwd_softmax(const float* weights, float* gw_inout, int B, int K, float temperature, float* rowsum,
+                              float* colsum, void* stream);
+int rqb200_gumbel_bwd_gx(float* acc_inout, const float* x, int64_t ldx, const float* E, const float* g_loss,
+                         int64_t gl_sB, const float* rowsum, float beta, int B, int D, void* stream);
+int rqb200_gumbel_bwd_gc(float* gC_inout, const float* C, const float* colsum, int K, int D, void* stream);
+/* modules/normalize.py:6-7 (F.normalize p=2) and its backward */
+int rqb200_l2norm_fwd(const float* x, float* y, float* norms, int B, int D, float eps, void* stream);
+int rqb200_l2norm_bwd(const float* gy, const float* y, const float* norms, float* gx, int B, int D, float eps,
+                      void* stream);
+
+/* ---- corpus id statistics (train_rqvae.py:279-289, modules/tokenizer/semids.py:94-108) ---------------- */
+int rqb200_sid_histogram(const int64_t* ids, int B, int L, int K, int64_t* hist /* [L,K], zeroed here */,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQB200_H */

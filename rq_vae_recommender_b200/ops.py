@@ -1,0 +1,433 @@
+"""torch.Tensor <-> librqb200 C-ABI marshalling and the autograd Functions built on it.
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every FLOP of the hot path
+runs in the hand-written kernels of csrc/.  CUDA tensors only -- CPU tensors raise (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+MODE_EVAL, MODE_GUMBEL, MODE_STE, MODE_ROTATION = 0, 1, 2, 3
+
+#: count of librqb200 kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.Rqb200Error("rq_vae_recommender_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                                   f"{t.device} tensor")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor whose last dim is unit-stride (row stride may exceed the width)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _ptr_array(ts: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = _p(t)
+    return arr
+
+
+def _check_codebooks(cbs: Sequence[torch.Tensor], D: int) -> List[torch.Tensor]:
+    out = [_f32c(c) for c in cbs]
+    K = out[0].shape[0]
+    for c in out:
+        if c.shape != (K, D):
+            raise ValueError(f"codebook shape {tuple(c.shape)} != ({K}, {D})")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- fused RQ chain
+def rq_forward(x: torch.Tensor, codebooks: Sequence[torch.Tensor], mode: int, beta: float, *,
+               want_ids=True, want_embeddings=False, want_residuals=False, want_sum=False, want_norms=False,
+               want_loss=False):
+    """All L Quantize levels in one launch (csrc/rq_simt.cu).  Returns a dict of the requested outputs;
+    embeddings / residuals come back as [L,B,D] (permute to the reference's [B,D,L] is a view)."""
+    _need_cuda(x, *codebooks)
+    lib = _lib.load()
+    x = _rows(x)
+    B, D = x.shape
+    cbs = _check_codebooks(codebooks, D)
+    K, L = cbs[0].shape[0], len(cbs)
+    dev = x.device
+    out = {}
+    ids = torch.empty((B, L), dtype=torch.int64, device=dev) if want_ids else None
+    emb = torch.empty((L, B, D), dtype=torch.float32, device=dev) if want_embeddings else None
+    res = torch.empty((L, B, D), dtype=torch.float32, device=dev) if want_residuals else None
+    esum = torch.empty((B, D), dtype=torch.float32, device=dev) if want_sum else None
+    norms = torch.empty((B, L), dtype=torch.float32, device=dev) if want_norms else None
+    loss = torch.empty((B,), dtype=torch.float32, device=dev) if want_loss else None
+    ws_bytes = lib.rqb200_rq_workspace_bytes(D, K, L)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rqb200_rq_forward(mode, _p(x), x.stride(0), _ptr_array(cbs), B, D, K, L, float(beta),
+                                         _p(ids), _p(emb), _p(res), _p(esum), _p(norms), _p(loss),
+                                         _p(ws), ws_bytes, _stream()), "rq_forward")
+    _count(3)
+    out.update(ids=ids, embeddings=emb, residuals=res, emb_sum=esum, emb_norms=norms, loss=loss)
+    return out
+
+
+def rq_tokenize(x: torch.Tensor, codebooks: Sequence[torch.Tensor]) -> torch.Tensor:
+    """sem_ids [B,L] int64 -- eval-mode hard argmin chain, exact fp32 kernel."""
+    return rq_forward(x, codebooks, MODE_EVAL, 0.0, want_ids=True)["ids"]
+
+
+class RqChainFunction(torch.autograd.Function):
+    """Differentiable fused chain (eval / STE / rotation-trick).
+
+    lean=True  -> (emb_sum [B,D], emb_norms [B,L], ids [B,L], loss [B])     what RqVae.forward consumes
+    lean=False -> (embeddings [L,B,D], residuals [L,B,D], ids [B,L], loss [B])   what get_semantic_ids returns
+    """
+
+    @staticmethod
+    def forward(ctx, x, mode, beta, lean, *codebooks):
+        xr = _rows(x)
+        cbs = _check_codebooks(codebooks, xr.shape[1])
+        o = rq_forward(xr, cbs, mode, beta, want_ids=True, want_embeddings=not lean, want_residuals=not lean,
+                       want_sum=lean, want_norms=lean, want_loss=True)
+        ctx.mode, ctx.beta, ctx.lean = mode, beta, lean
+        ctx.save_for_backward(xr, o["ids"], *cbs)
+        ctx.mark_non_differentiable(o["ids"])
+        if lean:
+            ctx.mark_non_differentiable(o["emb_norms"])
+            return o["emb_sum"], o["emb_norms"], o["ids"], o["loss"]
+        return o["embeddings"], o["residuals"], o["ids"], o["loss"]
+
+    @staticmethod
+    def backward(ctx, g_a, g_b, _g_ids, g_loss):
+        xr, ids, *cbs = ctx.saved_tensors
+        lib = _lib.load()
+        B, D = xr.shape
+        K, L = cbs[0].shape[0], len(cbs)
+        dev = xr.device
+
+        def f32(g):
+            return None if g is None else (g if g.dtype == torch.float32 else g.float())
+
+        g_a, g_loss = f32(g_a), f32(g_loss)
+        if ctx.lean:
+            g_emb, g_res = g_a, None
+            ge = (g_emb.stride(0), g_emb.stride(1), 0) if g_emb is not None else (0, 0, 0)
+            gr = (0, 0, 0)
+        else:
+            g_emb, g_res = g_a, f32(g_b)
+            ge = (g_emb.stride(1), g_emb.stride(2), g_emb.stride(0)) if g_emb is not None else (0, 0, 0)
+            gr = (g_res.stride(1), g_res.stride(2), g_res.stride(0)) if g_res is not None else (0, 0, 0)
+        g_x = torch.empty((B, D), dtype=torch.float32, device=dev)
+        need_cb = [ctx.needs_input_grad[4 + l] for l in range(L)]
+        g_cbs = [torch.zeros_like(c) if n else None for c, n in zip(cbs, need_cb)]
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqb200_rq_backward(ctx.mode, _p(xr), xr.stride(0), _ptr_array(cbs), _p(ids), B, D, K, L,
+                                              float(ctx.beta), _p(g_emb), *ge, _p(g_res), *gr, _p(g_loss),
+                                              g_loss.stride(0) if g_loss is not None else 0, _p(g_x),
+                                              _ptr_array(g_cbs), _stream()), "rq_backward")
+        _count(1)
+        return (g_x if ctx.needs_input_grad[0] else None, None, None, None, *g_cbs)
+
+
+# ---------------------------------------------------------------------------------------------- dense helpers
+def sgemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, relu=False,
+          mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, alpha=1.0, beta=0.0):
+    """out = epi(alpha * op(a) @ op(b) + beta*out) with the fp32 CUDA-core GEMM of csrc/dense.cu."""
+    lib = _lib.load()
+    a, b = _rows(a), _rows(b)
+    M, Ka = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    Kb, N = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if Ka != Kb:
+        raise ValueError(f"sgemm inner dims differ: {Ka} vs {Kb}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if mask is not None:
+        mask = _rows(mask)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.rqb200_sgemm(int(trans_a), int(trans_b), M, N, Ka, float(alpha), _p(a), a.stride(0), _p(b),
+                                    b.stride(0), float(beta), _p(out), out.stride(0), int(relu), _p(mask),
+                                    mask.stride(0) if mask is not None else 0, _stream()), "sgemm")
+    _count(1)
+    return out
+
+
+class MLPFunction(torch.autograd.Function):
+    """modules/encoder.py:23-38 as one autograd node: bias-free Linear+ReLU stack (ReLU fused in the GEMM
+    epilogue), optional final L2 normalisation (modules/normalize.py)."""
+
+    @staticmethod
+    def forward(ctx, x, normalize, *weights):
+        _need_cuda(x, *weights)
+        lib = _lib.load()
+        h = _rows(x)
+        ws = [_f32c(w) for w in weights]
+        acts = [h]
+        n = len(ws)
+        for i, w in enumerate(ws):
+            h = sgemm(h, w, trans_b=True, relu=(i != n - 1))
+            acts.append(h)
+        norms = None
+        if normalize:
+            y = torch.empty_like(h)
+            norms = torch.empty(h.shape[0], dtype=torch.float32, device=h.device)
+            with torch.cuda.device(h.device):
+                _lib.check(lib.rqb200_l2norm_fwd(_p(h), _p(y), _p(norms), h.shape[0], h.shape[1], 1e-12, _stream()),
+                           "l2norm_fwd")
+            _count(1)
+            acts.append(y)
+            h = y
+        ctx.normalize = normalize
+        ctx.n = n
+        ctx.save_for_backward(*acts, *ws, *([norms] if normalize else []))
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n = ctx.n
+        saved = ctx.saved_tensors
+        n_act = n + 1 + (1 if ctx.normalize else 0)
+        acts, ws = saved[:n_act], saved[n_act:n_act + n]
+        g = _f32c(g)
+        if ctx.normalize:
+            norms, y = saved[-1], acts[-1]
+            gx = torch.empty_like(g)
+            with torch.cuda.device(g.device):
+                _lib.check(lib.rqb200_l2norm_bwd(_p(g), _p(y), _p(norms), _p(gx), g.shape[0], g.shape[1], 1e-12,
+                                                 _stream()), "l2norm_bwd")
+            _count(1)
+            g = gx
+        g_ws = [None] * n
+        for i in range(n - 1, -1, -1):
+            h_in = acts[i]
+            if ctx.needs_input_grad[2 + i]:
+                g_ws[i] = sgemm(g, h_in, trans_a=True)                     # [out,B] @ [B,in]
+            if i > 0 or ctx.needs_input_grad[0]:
+                g = sgemm(g, ws[i], mask=h_in if i > 0 else None)          # [B,out] @ [out,in], ReLU' of layer i-1
+        return (g if ctx.needs_input_grad[0] else None, None, *g_ws)
+
+
+def l2norm_rows(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=-1) forward only (no autograd)."""
+    lib = _lib.load()
+    shp = x.shape
+    x2 = _f32c(x.reshape(-1, shp[-1]))
+    y = torch.empty_like(x2)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.rqb200_l2norm_fwd(_p(x2), _p(y), 0, x2.shape[0], x2.shape[1], float(eps), _stream()), "l2norm")
+    _count(1)
+    return y.reshape(shp)
+
+
+class L2NormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        lib = _lib.load()
+        shp = x.shape
+        x2 = _f32c(x.reshape(-1, shp[-1]))
+        y = torch.empty_like(x2)
+        norms = torch.empty(x2.shape[0], dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device):
+            _lib.check(lib.rqb200_l2norm_fwd(_p(x2), _p(y), _p(norms), x2.shape[0], x2.shape[1], float(eps), _stream()),
+                       "l2norm_fwd")
+        _count(1)
+        ctx.eps, ctx.shp = eps, shp
+        ctx.save_for_backward(y, norms)
+        return y.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        y, norms = ctx.saved_tensors
+        g2 = _f32c(g.reshape(y.shape))
+        gx = torch.empty_like(g2)
+        with torch.cuda.device(g2.device):
+            _lib.check(lib.rqb200_l2norm_bwd(_p(g2), _p(y), _p(norms), _p(gx), y.shape[0], y.shape[1], float(ctx.eps),
+                                             _stream()), "l2norm_bwd")
+        _count(1)
+        return gx.reshape(ctx.shp), None
+
+
+# ---------------------------------------------------------------------------------------------- Gumbel-softmax level
+class GumbelQuantizeFunction(torch.autograd.Function):
+    """One training-mode GUMBEL_SOFTMAX Quantize level (modules/quantize.py:113-136,157): returns
+    (emb [B,D], ids [B], loss [B]).  The uniform draw U is an input (the caller draws it with torch.rand on the
+    device, exactly where distributions/gumbel.py:10 does)."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, uniform, temperature, beta):
+        _need_cuda(x, codebook, uniform)
+        lib = _lib.load()
+        x, cb, u = _rows(x), _f32c(codebook), _f32c(uniform)
+        B, D = x.shape
+        K = cb.shape[0]
+        dev = x.device
+        st = _stream()
+        cc = torch.empty(K, dtype=torch.float32, device=dev)
+        ids = torch.empty(B, dtype=torch.int64, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        w = torch.empty((B, K), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqb200_row_sqnorm(_p(cb), K, D, _p(cc), st), "row_sqnorm")
+            dist = sgemm(x, cb, trans_b=True)                                    # x @ C^T
+            _lib.check(lib.rqb200_dist_finish(_p(dist), _p(x), x.stride(0), _p(cc), B, D, K, _p(ids), st), "dist")
+            _lib.check(lib.rqb200_gumbel_softmax_fwd(_p(dist), _p(u), _p(w), B, K, float(temperature), st), "softmax")
+            emb = sgemm(w, cb)                                                   # W @ C   (quantize.py:135)
+            _lib.check(lib.rqb200_gumbel_row_finish(_p(x), x.stride(0), _p(emb), B, D, float(beta), _p(loss), st),
+                       "row_finish")
+        _count(4)
+        ctx.temperature, ctx.beta = float(temperature), float(beta)
+        ctx.save_for_backward(x, cb, w, emb)
+        ctx.mark_non_differentiable(ids)
+        return emb, ids, loss
+
+    @staticmethod
+    def backward(ctx, g_emb, _g_ids, g_loss):
+        lib = _lib.load()
+        x, cb, w, emb = ctx.saved_tensors
+        B, D = x.shape
+        K = cb.shape[0]
+        dev = x.device
+        st = _stream()
+        g_emb = None if g_emb is None else (g_emb if g_emb.dtype == torch.float32 else g_emb.float())
+        g_loss = None if g_loss is None else (g_loss if g_loss.dtype == torch.float32 else g_loss.float())
+        gl_s = g_loss.stride(0) if g_loss is not None else 0
+        gE = torch.empty((B, D), dtype=torch.float32, device=dev)
+        rowsum = torch.empty(B, dtype=torch.float32, device=dev)
+        colsum = torch.empty(K, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqb200_gumbel_bwd_ge(_p(g_emb), g_emb.stride(0) if g_emb is not None else 0,
+                                                g_emb.stride(1) if g_emb is not None else 0, _p(g_loss), gl_s,
+                                                _p(x), x.stride(0), _p(emb), _p(gE), B, D, st), "bwd_ge")
+            gw = sgemm(gE, cb, trans_b=True)                                     # gW = gE @ C^T   [B,K]
+            _lib.check(lib.rqb200_gumbel_bwd_softmax(_p(w), _p(gw), B, K, ctx.temperature, _p(rowsum), _p(colsum), st),
+                       "bwd_softmax")                                            # gw now holds gdist
+            gx = sgemm(gw, cb)                                                   # gdist @ C       [B,D]
+            _lib.check(lib.rqb200_gumbel_bwd_gx(_p(gx), _p(x), x.stride(0), _p(emb), _p(g_loss), gl_s, _p(rowsum),
+                                                ctx.beta, B, D, st), "bwd_gx")
+            gc = None
+            if ctx.needs_input_grad[1]:
+                gc = sgemm(w, gE, trans_a=True)                                  # W^T @ gE        [K,D]
+                sgemm(gw, x, trans_a=True, out=gc, alpha=-2.0, beta=1.0)         # - 2 gdist^T @ x
+                _lib.check(lib.rqb200_gumbel_bwd_gc(_p(gc), _p(cb), _p(colsum), K, D, st), "bwd_gc")
+        _count(5)
+        return (gx if ctx.needs_input_grad[0] else None, gc, None, None, None)
+
+
+# ---------------------------------------------------------------------------------------------- k-means
+def kmeans_workspace(x: torch.Tensor, K: int):
+    lib = _lib.load()
+    D = x.shape[1]
+    dev = x.device
+    ws_bytes = lib.rqb200_rq_workspace_bytes(D, K, 1)
+    return dict(ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes=ws_bytes,
+                assign=torch.empty(x.shape[0], dtype=torch.int64, device=dev),
+                sums=torch.empty((K, D), dtype=torch.float64, device=dev),
+                counts=torch.empty(K, dtype=torch.int32, device=dev),
+                shift=torch.empty(1, dtype=torch.float32, device=dev))
+
+
+def kmeans_assign_accumulate(x: torch.Tensor, centroids: torch.Tensor, buf) -> None:
+    lib = _lib.load()
+    B, D = x.shape
+    K = centroids.shape[0]
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rqb200_kmeans_assign_accumulate(_p(x), x.stride(0), _p(centroids), B, D, K, _p(buf["assign"]),
+                                                       _p(buf["sums"]), _p(buf["counts"]), _p(buf["ws"]),
+                                                       buf["ws_bytes"], _stream()), "kmeans_assign_accumulate")
+    _count(3)
+
+
+def kmeans_finalize(x: torch.Tensor, centroids: torch.Tensor, buf, reseed_rows: Optional[torch.Tensor]) -> None:
+    lib = _lib.load()
+    K, D = centroids.shape
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rqb200_kmeans_finalize(_p(buf["sums"]), _p(buf["counts"]), _p(x), x.stride(0), _p(reseed_rows),
+                                              _p(centroids), K, D, _p(buf["shift"]), _stream()), "kmeans_finalize")
+    _count(1)
+
+
+# ---------------------------------------------------------------------------------------------- id statistics
+def sid_histogram(ids: torch.Tensor, K: int) -> torch.Tensor:
+    """[L,K] int64 code-usage counts of a [B,L] int64 id table (train_rqvae.py:285-289)."""
+    _need_cuda(ids)
+    lib = _lib.load()
+    ids = ids.contiguous()
+    B, L = ids.shape
+    hist = torch.empty((L, K), dtype=torch.int64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(lib.rqb200_sid_histogram(_p(ids), B, L, K, _p(hist), _stream()), "sid_histogram")
+    _count(1)
+    return hist
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core tokeniser
+def tc_supported(D: int, K: int, L: int) -> bool:
+    return bool(_lib.load().rqb200_tokenize_tc_supported(D, K, L))
+
+
+class TcState:
+    """Device-side prepared codebooks for the tcgen05 tokeniser (fp16 copies, norms, Gram tables)."""
+
+    def __init__(self, codebooks: Sequence[torch.Tensor]):
+        lib = _lib.load()
+        cbs = _check_codebooks(codebooks, codebooks[0].shape[1])
+        self.K, self.D = cbs[0].shape
+        self.L = len(cbs)
+        if not lib.rqb200_tokenize_tc_supported(self.D, self.K, self.L):
+            raise _lib.Rqb200Error(f"tcgen05 tokeniser does not support D={self.D} K={self.K} L={self.L}")
+        nbytes = lib.rqb200_tokenize_tc_state_bytes(self.D, self.K, self.L)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=cbs[0].device)
+        self.nbytes = nbytes
+        self.codebooks = cbs            # keep alive: the re-rank reads the fp32 originals
+        with torch.cuda.device(self.buf.device):
+            _lib.check(lib.rqb200_tokenize_tc_prepare(_ptr_array(cbs), self.D, self.K, self.L, _p(self.buf), nbytes,
+                                                      _stream()), "tokenize_tc_prepare")
+        _count(3)
+
+
+def rq_tokenize_tc(x: torch.Tensor, codebooks=None, state: Optional[TcState] = None, stats=None) -> torch.Tensor:
+    """sem_ids [B,L] int64 via the tcgen05 candidate filter + exact fp32 re-rank (csrc/rq_tc.cu)."""
+    _need_cuda(x)
+    lib = _lib.load()
+    if state is None:
+        state = TcState(codebooks)
+    x = _rows(x)
+    B, D = x.shape
+    ids = torch.empty((B, state.L), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rqb200_tokenize_tc_run(_p(x), x.stride(0), B, _p(state.buf), D, state.K, state.L, _p(ids),
+                                              _p(stats), _stream()), "tokenize_tc_run")
+    _count(1)
+    return ids

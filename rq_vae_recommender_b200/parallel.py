@@ -1,0 +1,199 @@
+"""Multi-GPU and host-facing drivers of the hot path.
+
+* ``CorpusTokenizer``: items -> semantic ids.  Rows are independent, so a corpus is cut into contiguous shards,
+  one per rank, tokenised with no data-path collective, and only the [N/G, L] id blocks are all-gathered.
+* ``sharded_kmeans_init_``: k-means codebook init over row shards; per Lloyd iteration one all-reduce of the
+  [K, D] fp64 sums + [K] counts (one flat buffer), identical centroid update on every rank.
+* ``codebook_usage``: [L,K] usage counts, all-reduced.
+
+torch.distributed is the plumbing (NCCL on GPUs; the same code runs on gloo for the CPU logic tests with the
+kernel calls injected).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of n rows for `rank` (first n % world ranks get one extra row)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class CorpusTokenizer:
+    """Frozen codebooks -> ids.  ``use_tc`` selects the tcgen05 filter + exact re-rank kernel (prepared once)."""
+
+    def __init__(self, codebooks: Sequence[torch.Tensor], use_tc: Optional[bool] = None,
+                 encoder: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, chunk_rows: int = 16384):
+        self.codebooks = [c.detach() for c in codebooks]
+        self.K, self.D = self.codebooks[0].shape
+        self.L = len(self.codebooks)
+        if use_tc is None:
+            use_tc = ops.tc_supported(self.D, self.K, self.L)
+        self.use_tc = bool(use_tc)
+        self.state = ops.TcState(self.codebooks) if self.use_tc else None
+        self.encoder = encoder
+        self.chunk_rows = chunk_rows
+        self._copy_stream = None
+
+    # ---- device resident rows
+    @torch.no_grad()
+    def tokenize_device(self, x: torch.Tensor) -> torch.Tensor:
+        if self.encoder is not None:
+            x = self.encoder(x)
+        if self.use_tc:
+            return ops.rq_tokenize_tc(x, state=self.state)
+        return ops.rq_tokenize(x, self.codebooks)
+
+    # ---- host rows in, host ids out (the reference's semids.py:93 copies every 512-row batch H->D)
+    @torch.no_grad()
+    def tokenize_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Double-buffered: chunk i+1 is copied host->device on a side stream while chunk i is quantised."""
+        n = x_host.shape[0]
+        dev = self.codebooks[0].device
+        if out is None:
+            out = torch.empty((n, self.L), dtype=torch.int64).pin_memory()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        bufs, evs = [], []
+        starts = list(range(0, n, self.chunk_rows))
+        for s in starts:
+            with torch.cuda.stream(cs):
+                xb = x_host[s:s + self.chunk_rows].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            bufs.append(xb)
+            evs.append(ev)
+        for s, xb, ev in zip(starts, bufs, evs):
+            main.wait_event(ev)
+            xb.record_stream(main)
+            ids = self.tokenize_device(xb)
+            out[s:s + self.chunk_rows].copy_(ids, non_blocking=True)
+        main.synchronize()
+        return out
+
+    # ---- corpus sharded over the ranks of `group`
+    @torch.no_grad()
+    def tokenize_sharded(self, x_local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+        """x_local = rows shard_bounds(n_total, world, rank) of the corpus; returns the full [n_total, L] table on
+        every rank (all-gather of int32 id blocks, corpus order)."""
+        import torch.distributed as dist
+        ids_local = self.tokenize_device(x_local)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return ids_local
+        return all_gather_rows(ids_local.to(torch.int32), n_total, group).to(torch.int64)
+
+    def measured_traffic_bytes(self):
+        return None
+
+
+def all_gather_rows(block: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (sizes given by shard_bounds) in rank order on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(n_total, world, r) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((mx,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+    pad[: block.shape[0]] = block
+    gathered = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad, group=group)
+    return torch.cat([g[: hi - lo] for g, (lo, hi) in zip(gathered, sizes)], dim=0)
+
+
+def codebook_usage(sem_ids_local: torch.Tensor, K: int, group=None, hist_fn=None) -> torch.Tensor:
+    """[L,K] int64 usage counts over all shards (train_rqvae.py:285-289 semantics), all-reduced."""
+    import torch.distributed as dist
+    hist = (hist_fn or ops.sid_histogram)(sem_ids_local, K)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, group=group)
+    return hist
+
+
+# ------------------------------------------------------------------------------------------------ sharded k-means
+def _default_assign_accumulate(x, centroids, buf):
+    ops.kmeans_assign_accumulate(x, centroids, buf)
+
+
+def _default_finalize(x, centroids, buf, reseed):
+    ops.kmeans_finalize(x, centroids, buf, reseed)
+
+
+@torch.no_grad()
+def sharded_kmeans(x_local: torch.Tensor, k: int, n_total: int, group=None, max_iters: Optional[int] = None,
+                   stop_threshold: float = 1e-10, assign_accumulate=None, finalize=None, make_buf=None):
+    """init/kmeans.py semantics over a row-sharded x (every rank holds shard_bounds(n_total, world, rank)).
+
+    RNG: every rank draws the SAME global ``np.random.choice(n_total, k)`` (seed numpy identically on all ranks,
+    as for a single process) and, for empty clusters, rank 0 draws ``torch.randint(0, n_total)`` and broadcasts.
+    Rows named by a global index are fetched from their owner with a sum all-reduce of a one-hot-masked [k,D]
+    buffer.  Returns (centroids [k,D], local assignment, n_iters)."""
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    lo, hi = shard_bounds(n_total, world, rank)
+    assert x_local.shape[0] == hi - lo, (x_local.shape, lo, hi)
+    dev = x_local.device
+    D = x_local.shape[1]
+    assign_accumulate = assign_accumulate or _default_assign_accumulate
+    finalize = finalize or _default_finalize
+    buf = (make_buf or ops.kmeans_workspace)(x_local, k)
+
+    def fetch_rows(global_idx: torch.Tensor) -> torch.Tensor:
+        """rows x[global_idx] ([m] int64 on host; -1 = none) gathered from their owners -> [m, D] on every rank"""
+        out = torch.zeros((len(global_idx), D), dtype=torch.float32, device=dev)
+        mine = (global_idx >= lo) & (global_idx < hi)
+        if mine.any():
+            sel = torch.nonzero(mine).flatten()
+            out[sel.to(dev)] = x_local[(global_idx[sel] - lo).to(dev)]
+        if distributed:
+            dist.all_reduce(out, group=group)
+        return out
+
+    init_idx = torch.from_numpy(np.random.choice(n_total, k, replace=False).astype(np.int64))
+    centroids = fetch_rows(init_idx).contiguous()
+
+    i = 0
+    n_iters = 0
+    while max_iters is None or i < max_iters:
+        assign_accumulate(x_local, centroids, buf)
+        if distributed:
+            flat = torch.cat([buf["sums"].reshape(-1), buf["counts"].to(torch.float64)])
+            dist.all_reduce(flat, group=group)
+            buf["sums"].copy_(flat[: k * D].view(k, D))
+            buf["counts"].copy_(flat[k * D:].to(torch.int32))
+        counts_h = buf["counts"].cpu()
+        empty = torch.nonzero(counts_h == 0).flatten()
+        old = centroids.clone()
+        finalize(x_local, centroids, buf, None)            # means; empty clusters keep their old centroid for now
+        if len(empty):
+            if n_total <= 0:
+                raise ValueError("Can not choose random element from x, x is empty")
+            draws = torch.tensor([int(torch.randint(0, n_total, (1,))) for _ in empty.tolist()], dtype=torch.int64)
+            if distributed:
+                d = draws.to(dev)
+                dist.broadcast(d, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                draws = d.cpu()
+            centroids[empty.to(dev)] = fetch_rows(draws)
+        shift = float((centroids - old).norm(dim=1).max().item())
+        n_iters = i + 1
+        if shift < stop_threshold:
+            break
+        i += 1
+    return centroids, buf["assign"], n_iters
+
+
+@torch.no_grad()
+def sharded_kmeans_init_(weight: torch.Tensor, x_local: torch.Tensor, n_total: int, group=None, **kw) -> None:
+    """kmeans_init_(tensor, x) (init/kmeans.py:8-15) for a row-sharded x: every rank ends with the same codebook."""
+    centroids, _, _ = sharded_kmeans(x_local, weight.shape[0], n_total, group, **kw)
+    weight.data.copy_(centroids)
