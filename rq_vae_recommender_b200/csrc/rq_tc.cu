@@ -1,17 +1,577 @@
-// Tensor-core (tcgen05) tokeniser: candidate filter on fp16 tensor cores + exact fp32 re-rank.
-// (placeholder translation unit while the kernel is being brought up: reports "unsupported" for every shape so
-//  callers use the exact CUDA-core kernel of rq_simt.cu)
+// Tensor-core tokeniser for sm_100a: tcgen05 fp16 candidate filter + exact fp32 re-rank.
+//
+// Result contract: identical to rqb200_rq_forward(mode = EVAL, ids only) -- the hard-argmin chain of
+// modules/quantize.py:113-128,159-161 x L + modules/rqvae.py:125-132 (what semids.py:125 consumes).
+//
+// Why tensor cores: the distance term x.c^T is 2*D*K*L = 1.18 MFLOP per 3 KB item (381 FLOP/B);
+// on CUDA cores the pass is ~30x compute bound.  Why it is still exact: the fp16 product only FILTERS.
+//   S_l[b,k]  = fp16(x_b) . fp16(c_{l,k})            (tcgen05.mma, fp32 accumulate in TMEM; exact power-of-two scales)
+//   score_l   = cc_{l,k} - 2 (S_l - sum_{j<l} G_{jl}[id_j, k])     (G = fp32 Gram tables C_j C_l^T, so every level is
+//               scored from the ONE fp16 image of x: the residual never has to be re-quantised or re-staged)
+//   candidates = { k : score <= min + 4 eps_b }      eps_b bounds the fp16 rounding of the dot product (see tc_margin)
+//   |candidates| == 1  -> that code is the exact argmin;  else the candidates are re-scored with the exact fp32
+//   arithmetic of the CUDA-core kernel (sequential fp32 residual, (xx + cc) - 2 dot, first index wins ties).
+//
+// Kernel structure (persistent, one CTA per SM, 128 rows per tile, warp specialised):
+//   warp 0       B producer  : 16 KB pre-swizzled fp16 codebook blocks -> smem ring, TMA bulk copies + mbarriers
+//   warp 1       MMA issuer  : one thread issues tcgen05.mma (M128 N128 K16), accumulators double-buffered in TMEM
+//   warps 2-9    converters  : 128-bit coalesced fp32 loads of x -> fp16 -> K-major SWIZZLE_128B smem (A operand),
+//                              refilled chunk by chunk as the last level releases it (x is read from HBM once)
+//   warps 10-13  epilogue    : tcgen05.ld scores, Gram correction, candidate detection, warp-cooperative exact re-rank
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <cmath>
 
-extern "C" size_t rqb200_tokenize_tc_state_bytes(int D, int K, int L) { return 0; }
-extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) { return 0; }
+extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                            const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int relu,
+                            const float* mask, int64_t ldmask, void* stream);
+
+#define TC_K 256          // codes per level (fixed)
+#define TC_BM 128         // rows per tile
+#define TC_KC 64          // fp16 elements per 128-byte swizzle row
+#define TC_MAX_D 768
+#define TC_MAX_KC (TC_MAX_D / TC_KC)
+#define TC_BSTAGES 2
+#define TC_BSTAGE_BYTES (128 * TC_KC * 2)   // 128 codes x 64 k x fp16 = 16 KB
+#define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
+#define TC_NCONV_WARPS 8
+#define TC_NEPI_WARPS 4
+#define TC_THREADS ((2 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)
+#define TC_Z 6.0f         // margin multiplier on the statistical fp16 rounding bound
+
+struct TcLevelConst {
+  float sc;      // power-of-two scale applied to the codebook before fp16 conversion
+  float c4max;   // max_k sqrt(sum_d c^4)
+  float c1max;   // max_k sum_d |c|
+  float c2max;   // max_k ||c||_2
+  float gerr;    // bound on the fp32 rounding of the Gram corrections of this level
+  float pad[3];
+};
+
+struct TcHeader {
+  TcLevelConst lv[RQB_MAX_LEVELS];
+  unsigned int amax_bits[RQB_MAX_LEVELS];  // scratch of prepare
+  unsigned int c4_bits[RQB_MAX_LEVELS];
+  unsigned int c1_bits[RQB_MAX_LEVELS];
+  unsigned int c2_bits[RQB_MAX_LEVELS];
+};
+
+static size_t tc_off_cc(int L) { return rqb_round_up(sizeof(TcHeader), 256); }
+static size_t tc_off_gram(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
+static size_t tc_off_cbptr(int L) { return tc_off_gram(L) + (size_t)(L * (L - 1) / 2) * TC_K * TC_K * 4; }
+static size_t tc_off_blob(int L) { return rqb_round_up(tc_off_cbptr(L) + RQB_MAX_LEVELS * 8, 1024); }
+
+extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) {
+  return (K == TC_K && D >= TC_KC && D <= TC_MAX_D && D % TC_KC == 0 && L >= 1 && L <= RQB_MAX_LEVELS) ? 1 : 0;
+}
+
+extern "C" size_t rqb200_tokenize_tc_state_bytes(int D, int K, int L) {
+  if (!rqb200_tokenize_tc_supported(D, K, L)) return 0;
+  return tc_off_blob(L) + (size_t)L * 2 * (D / TC_KC) * TC_BSTAGE_BYTES;
+}
+
+// ------------------------------------------------------------------------------------------------ prepare
+__global__ void tc_prep_stats_kernel(const float* const* cbs, int D, TcHeader* hdr, float* cc) {
+  const int l = blockIdx.y;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (k >= TC_K) return;
+  const float* c = cbs[l] + (int64_t)k * D;
+  float s2 = 0.f, s4 = 0.f, s1 = 0.f, mx = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = c[d], v2 = v * v;
+    s2 = fmaf(v, v, s2);
+    s4 = fmaf(v2, v2, s4);
+    s1 += fabsf(v);
+    mx = fmaxf(mx, fabsf(v));
+  }
+  s2 = warp_sum(s2); s4 = warp_sum(s4); s1 = warp_sum(s1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) {
+    cc[l * TC_K + k] = s2;
+    atomicMax(&hdr->amax_bits[l], __float_as_uint(mx));
+    atomicMax(&hdr->c4_bits[l], __float_as_uint(sqrtf(s4)));
+    atomicMax(&hdr->c1_bits[l], __float_as_uint(s1));
+    atomicMax(&hdr->c2_bits[l], __float_as_uint(sqrtf(s2)));
+  }
+}
+
+__global__ void tc_prep_consts_kernel(TcHeader* hdr, int L) {
+  const int l = threadIdx.x;
+  if (l >= L) return;
+  const float amax = __uint_as_float(hdr->amax_bits[l]);
+  float sc = 1.f;
+  if (amax > 0.f && isfinite(amax)) {
+    int e;
+    frexpf(amax, &e);          // amax = m * 2^e, m in [0.5, 1)
+    e = max(-60, min(60, e));
+    sc = ldexpf(1.f, -e);      // amax * sc in [0.5, 1)
+  }
+  TcLevelConst& c = hdr->lv[l];
+  c.sc = sc;
+  c.c4max = __uint_as_float(hdr->c4_bits[l]);
+  c.c1max = __uint_as_float(hdr->c1_bits[l]);
+  c.c2max = __uint_as_float(hdr->c2_bits[l]);
+  float g = 0.f;
+  for (int j = 0; j < l; ++j) g += __uint_as_float(hdr->c2_bits[j]);
+  c.gerr = 3.8e-6f * g * c.c2max;   // 2^-18 * sum_j ||e_j|| ||c||: fp32 dot of length <= 768, generous
+}
+
+// Bblob[(l*2+h)*nkc + kc] = 16 KB smem image of codes [128h, 128h+128) x k [64kc, 64kc+64):
+// K-major, 128 B per code row, 16-byte chunks XOR-swizzled with (row & 7)  (UMMA SWIZZLE_128B canonical layout)
+__global__ void tc_prep_blob_kernel(const float* const* cbs, int D, const TcHeader* hdr, __half* blob) {
+  const int nkc = D / TC_KC;
+  const int blk = blockIdx.x;  // (l*2+h)*nkc + kc
+  const int kc = blk % nkc, h = (blk / nkc) & 1, l = blk / (2 * nkc);
+  const float sc = hdr->lv[l].sc;
+  const float* c = cbs[l];
+  __half* out = blob + (size_t)blk * (TC_BSTAGE_BYTES / 2);
+  for (int i = threadIdx.x; i < 128 * TC_KC; i += blockDim.x) {
+    const int n = i / TC_KC, k = i % TC_KC;
+    const float v = c[(int64_t)(h * 128 + n) * D + kc * TC_KC + k] * sc;
+    const int chunk = (k >> 3) ^ (n & 7);
+    out[n * 64 + chunk * 8 + (k & 7)] = __float2half_rn(v);
+  }
+}
+
 extern "C" int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, int K, int L, void* state,
                                           size_t state_bytes, void* stream) {
-  rqb_set_error("tokenize_tc: shape D=%d K=%d L=%d not supported", D, K, L);
-  return RQB_ERR_UNSUPPORTED;
+  if (!rqb200_tokenize_tc_supported(D, K, L)) {
+    rqb_set_error("tokenize_tc: shape D=%d K=%d L=%d not supported (need K=256, D %% 64 == 0, 64 <= D <= 768)", D, K, L);
+    return RQB_ERR_UNSUPPORTED;
+  }
+  RQB_CHECK_ARG(codebooks && state, "tokenize_tc_prepare: null pointer");
+  if (state_bytes < rqb200_tokenize_tc_state_bytes(D, K, L)) {
+    rqb_set_error("tokenize_tc_prepare: state too small");
+    return RQB_ERR_WORKSPACE;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* base = reinterpret_cast<char*>(state);
+  TcHeader* hdr = reinterpret_cast<TcHeader*>(base);
+  float* cc = reinterpret_cast<float*>(base + tc_off_cc(L));
+  float* gram = reinterpret_cast<float*>(base + tc_off_gram(L));
+  const float** cbptr = reinterpret_cast<const float**>(base + tc_off_cbptr(L));
+  __half* blob = reinterpret_cast<__half*>(base + tc_off_blob(L));
+  RQB_CUDA(cudaMemsetAsync(hdr, 0, sizeof(TcHeader), st));
+  RQB_CUDA(cudaMemcpyAsync(cbptr, codebooks, sizeof(float*) * L, cudaMemcpyHostToDevice, st));
+  tc_prep_stats_kernel<<<dim3(TC_K / 8, L), 256, 0, st>>>(cbptr, D, hdr, cc);
+  RQB_LAUNCH_CHECK();
+  tc_prep_consts_kernel<<<1, 32, 0, st>>>(hdr, L);
+  RQB_LAUNCH_CHECK();
+  tc_prep_blob_kernel<<<L * 2 * (D / TC_KC), 256, 0, st>>>(cbptr, D, hdr, blob);
+  RQB_LAUNCH_CHECK();
+  for (int l = 1; l < L; ++l)
+    for (int j = 0; j < l; ++j) {
+      float* g = gram + (size_t)(l * (l - 1) / 2 + j) * TC_K * TC_K;
+      int rc = rqb200_sgemm(0, 1, TC_K, TC_K, D, 1.f, codebooks[j], D, codebooks[l], D, 0.f, g, TC_K, 0, nullptr, 0, stream);
+      if (rc) return rc;
+    }
+  return RQB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B: 8 rows x 128 B)
+// | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+struct TcParams {
+  const float* x;
+  int64_t ldx;
+  int B, D, L, nkc, ntiles;
+  const TcHeader* hdr;
+  const float* cc;      // [L][256]
+  const float* gram;    // [L(L-1)/2][256][256]
+  const float* const* cb;  // device array of L fp32 codebook pointers (exact re-rank)
+  const unsigned char* blob;
+  int64_t* ids;         // [B][L]
+  int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
+  float sx;             // power-of-two scale applied to x before fp16 conversion
+};
+
+struct TcSmemMisc {
+  uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
+  uint64_t b_full[TC_BSTAGES], b_empty[TC_BSTAGES];
+  uint64_t t_full[2], t_empty[2];
+  uint64_t rowinfo_free;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float2 rowinfo[TC_BM];  // (sum x^4, sum x^2) of the tile being scored
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
+  unsigned char* sB = tsm + TC_MAX_KC * TC_ACHUNK_BYTES;           // [TC_BSTAGES][16 KB]
+  TcSmemMisc* ms = reinterpret_cast<TcSmemMisc*>(sB + TC_BSTAGES * TC_BSTAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkc = p.nkc, L = p.L;
+
+  if (tid == 0) {
+    if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
+    for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], TC_NCONV_WARPS * 32); mbar_init(&ms->a_empty[i], 1); }
+    for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], TC_NEPI_WARPS * 32); }
+    mbar_init(&ms->rowinfo_free, TC_NEPI_WARPS * 32);
+    fence_mbar_init();
+  }
+  if (warp == 1) tc_alloc(&ms->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ms->tmem_base;
+
+  if (warp == 0) {
+    // ============================================================== B producer
+    if (lane == 0) {
+      uint32_t s = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+        for (int l = 0; l < L; ++l)
+          for (int h = 0; h < 2; ++h)
+            for (int kc = 0; kc < nkc; ++kc, ++s) {
+              const uint32_t st = s % TC_BSTAGES, u = s / TC_BSTAGES;
+              mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);
+              mbar_expect_tx(&ms->b_full[st], TC_BSTAGE_BYTES);
+              bulk_g2s(sB + st * TC_BSTAGE_BYTES, p.blob + (size_t)((l * 2 + h) * nkc + kc) * TC_BSTAGE_BYTES,
+                       TC_BSTAGE_BYTES, &ms->b_full[st]);
+            }
+    }
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc_idesc(128, 128);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      uint32_t s = 0, g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it)
+        for (int l = 0; l < L; ++l, ++g) {
+          const uint32_t buf = g & 1, u = g >> 1;
+          mbar_wait_guarded(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          tc_fence_after();
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t d_tmem = tmem + buf * 256 + h * 128;
+            for (int kc = 0; kc < nkc; ++kc, ++s) {
+              if (l == 0 && h == 0) mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
+              const uint32_t st = s % TC_BSTAGES;
+              mbar_wait_guarded(&ms->b_full[st], (s / TC_BSTAGES) & 1, 4);
+              tc_fence_after();
+              const uint64_t adesc = tc_smem_desc(a_base + kc * TC_ACHUNK_BYTES);
+              const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < TC_KC / 16; ++j)   // K=16 per instruction: +32 B inside the 128 B swizzle row
+                tc_mma_f16(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kc | j) != 0);
+              tc_commit(&ms->b_empty[st]);
+              if (l == L - 1 && h == 1) tc_commit(&ms->a_empty[kc]);
+            }
+          }
+          tc_commit(&ms->t_full[buf]);
+        }
+    }
+  } else if (warp < 2 + TC_NCONV_WARPS) {
+    // ============================================================== converters: x fp32 -> fp16 swizzled A chunks
+    const int cw = warp - 2;                 // rows 16*cw .. 16*cw+15
+    const int sub = lane >> 4, q = lane & 15;  // lane -> (row parity, float4 index inside the 64-float chunk row)
+    const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int row_base = tile * TC_BM + cw * 16;
+      float s4[8], s2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s4[i] = 0.f; s2[i] = 0.f; }
+      float4 v[8];
+      auto load_chunk = [&](int kc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + 2 * i + sub;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < p.B) {
+            const float* src = p.x + (int64_t)row * p.ldx + kc * TC_KC + q * 4;
+            if (vec_ok) v[i] = ldg_stream(reinterpret_cast<const float4*>(src));
+            else { v[i].x = __ldg(src); v[i].y = __ldg(src + 1); v[i].z = __ldg(src + 2); v[i].w = __ldg(src + 3); }
+          }
+        }
+      };
+      load_chunk(0);
+      for (int kc = 0; kc < nkc; ++kc) {
+        float4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = v[i];
+        if (kc + 1 < nkc) load_chunk(kc + 1);          // prefetch the next chunk while this one is converted
+        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);      // the last level of the previous tile released this chunk
+        unsigned char* dst = sA + kc * TC_ACHUNK_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = cw * 16 + 2 * i + sub;
+          const float4 a = cur[i];
+          const float a2x = a.x * a.x, a2y = a.y * a.y, a2z = a.z * a.z, a2w = a.w * a.w;
+          s2[i] += (a2x + a2y) + (a2z + a2w);
+          s4[i] += (a2x * a2x + a2y * a2y) + (a2z * a2z + a2w * a2w);
+          const __half2 h0 = __floats2half2_rn(a.x * p.sx, a.y * p.sx);
+          const __half2 h1 = __floats2half2_rn(a.z * p.sx, a.w * p.sx);
+          // fp16 overflow / non-finite input: poison the row statistics -> every code becomes a candidate
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&h0), b1 = *reinterpret_cast<const uint32_t*>(&h1);
+          if (((b0 & 0x7c00u) == 0x7c00u) || ((b0 & 0x7c000000u) == 0x7c000000u) || ((b1 & 0x7c00u) == 0x7c00u) ||
+              ((b1 & 0x7c000000u) == 0x7c000000u))
+            s4[i] = INFINITY;
+          const uint32_t off = r * 128 + ((((uint32_t)q >> 1) ^ (r & 7)) << 4) + (q & 1) * 8;
+          *reinterpret_cast<uint2*>(dst + off) = make_uint2(b0, b1);
+        }
+        if (kc == nkc - 1) {
+          // row statistics for the margin: reduce over the 16 lanes that share a row, publish before the last arrive
+          mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], o);
+              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+            }
+            if (q == 0) ms->rowinfo[cw * 16 + 2 * i + sub] = make_float2(s4[i], s2[i]);
+          }
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&ms->a_full[kc]);
+      }
+    }
+  } else {
+    // ============================================================== epilogue: scores -> candidates -> exact re-rank -> ids
+    const int ew = warp - (2 + TC_NCONV_WARPS);
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+    const int r_local = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    (void)ew;
+    uint32_t g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int row = tile * TC_BM + r_local;
+      const bool valid = row < p.B;
+      uint64_t idpack = 0;          // 8 bits per level
+      float x4s = 0.f, x2s = 0.f;
+      for (int l = 0; l < L; ++l, ++g) {
+        const uint32_t buf = g & 1, u = g >> 1;
+        mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
+        tc_fence_after();
+        if (l == 0) {
+          const float2 ri = ms->rowinfo[r_local];
+          x4s = ri.x; x2s = ri.y;
+          mbar_arrive(&ms->rowinfo_free);
+        }
+        // ---- margin (see DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|
+        const TcLevelConst lc = p.hdr->lv[l];
+        const float x2n = sqrtf(x2s);
+        const float sig = 4.8828125e-4f * 0.81649658f * sqrtf(sqrtf(x4s) * lc.c4max);          // u=2^-11, sqrt(2/3)
+        const float flo = 2.98023224e-8f * (lc.c1max / p.sx + sqrtf((float)p.D) * x2n / lc.sc);  // fp16 subnormal floor
+        const float acc = 7.62939453e-6f * x2n * lc.c2max;                                      // 64 * 2^-23 accumulate
+        const float eps = TC_Z * sig + flo + acc + lc.gerr;
+        const float margin = 4.f * eps;
+        const float inv = 1.f / (p.sx * lc.sc);
+        const float* ccl = p.cc + l * TC_K;
+        const uint32_t tcol = tmem + lane_addr + buf * 256;
+
+        float m1 = INFINITY, m2 = INFINITY;
+        int i1 = 0;
+        uint32_t mask[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mask[c] = 0;
+
+        auto scan = [&](bool second) {
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            float sv[32];
+            tc_ld32(tcol + c * 32, sv);
+            uint32_t mw = 0;
+            if (valid) {
+#pragma unroll
+              for (int v4 = 0; v4 < 8; ++v4) {
+                const float4 cc4 = __ldg(reinterpret_cast<const float4*>(ccl + c * 32 + v4 * 4));
+                float4 corr = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < l; ++j) {
+                  const int idj = (int)((idpack >> (8 * j)) & 0xff);
+                  const float4 gj = __ldg(reinterpret_cast<const float4*>(
+                      p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + idj) * TC_K + c * 32 + v4 * 4));
+                  corr.x += gj.x; corr.y += gj.y; corr.z += gj.z; corr.w += gj.w;
+                }
+                const float a0 = cc4.x - 2.f * (sv[v4 * 4 + 0] * inv - corr.x);
+                const float a1 = cc4.y - 2.f * (sv[v4 * 4 + 1] * inv - corr.y);
+                const float a2 = cc4.z - 2.f * (sv[v4 * 4 + 2] * inv - corr.z);
+                const float a3 = cc4.w - 2.f * (sv[v4 * 4 + 3] * inv - corr.w);
+                const float av[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int k = c * 32 + v4 * 4 + e;
+                  if (!second) {
+                    if (av[e] < m1) { m2 = m1; m1 = av[e]; i1 = k; }
+                    else if (av[e] < m2) { m2 = av[e]; }
+                  } else {
+                    if (!(av[e] > m1 + margin)) mw |= 1u << (v4 * 4 + e);
+                  }
+                }
+              }
+            }
+            if (second) mask[c] = mw;
+          }
+        };
+        scan(false);
+        bool flagged = valid && !(m2 > m1 + margin);
+        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+        if (fl) scan(true);
+        tc_fence_before();
+        mbar_arrive(&ms->t_empty[buf]);     // accumulator buffer may be overwritten by level l+2
+
+        int my_id = i1;
+        // ---- warp-cooperative exact re-rank of the flagged rows (same arithmetic as rq_simt.cu)
+        uint32_t todo = fl;
+        int n_cand = 0;
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int rrow = __shfl_sync(0xffffffffu, row, src);
+          const uint32_t idlo = __shfl_sync(0xffffffffu, (uint32_t)idpack, src);
+          const uint32_t idhi = __shfl_sync(0xffffffffu, (uint32_t)(idpack >> 32), src);
+          const uint64_t rid = ((uint64_t)idhi << 32) | idlo;
+          float res[TC_MAX_D / 32];
+          const float* xr = p.x + (int64_t)rrow * p.ldx;
+#pragma unroll
+          for (int i = 0; i < TC_MAX_D / 32; ++i) res[i] = (i * 32 < p.D) ? __ldg(xr + i * 32 + lane) : 0.f;
+          for (int j = 0; j < l; ++j) {
+            const float* e = p.cb[j] + (int64_t)((rid >> (8 * j)) & 0xff) * p.D;
+#pragma unroll
+            for (int i = 0; i < TC_MAX_D / 32; ++i)
+              if (i * 32 < p.D) res[i] = res[i] - __ldg(e + i * 32 + lane);     // rqvae.py:130, level order
+          }
+          float xx = 0.f;
+#pragma unroll
+          for (int i = 0; i < TC_MAX_D / 32; ++i) xx = fmaf(res[i], res[i], xx);
+          xx = warp_sum(xx);
+          float best = INFINITY;
+          int besti = 0x7fffffff;
+          const float* cl = p.cb[l];
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {
+            uint32_t mw = __shfl_sync(0xffffffffu, mask[c], src);
+            while (mw) {
+              const int k = c * 32 + __ffs(mw) - 1;
+              mw &= mw - 1;
+              const float* ck = cl + (int64_t)k * p.D;
+              float dot = 0.f;
+#pragma unroll
+              for (int i = 0; i < TC_MAX_D / 32; ++i)
+                if (i * 32 < p.D) dot = fmaf(res[i], __ldg(ck + i * 32 + lane), dot);
+              dot = warp_sum(dot);
+              const float dist = (xx + __ldg(ccl + k)) - 2.f * dot;             // quantize.py:113-117
+              if (dist < best) { best = dist; besti = k; }
+              ++n_cand;
+            }
+          }
+          if (besti > 255) besti = __shfl_sync(0xffffffffu, i1, src);  // all-NaN row: keep the filter's pick
+          if (lane == src) my_id = besti;
+        }
+        if (p.stats && lane == 0 && fl) {
+          atomicAdd(p.stats + 0, __popc(fl));
+          atomicAdd(p.stats + 1, n_cand);
+          atomicAdd(p.stats + 2, 32);
+        }
+        idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
+        if (valid) p.ids[(int64_t)row * L + l] = my_id;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem, 512);
+  }
+}
+
 extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const void* state, int D, int K, int L,
                                       int64_t* ids, int* stats, void* stream) {
-  rqb_set_error("tokenize_tc: shape D=%d K=%d L=%d not supported", D, K, L);
-  return RQB_ERR_UNSUPPORTED;
+  if (!rqb200_tokenize_tc_supported(D, K, L)) {
+    rqb_set_error("tokenize_tc: shape D=%d K=%d L=%d not supported", D, K, L);
+    return RQB_ERR_UNSUPPORTED;
+  }
+  RQB_CHECK_ARG(B >= 0 && ldx >= D, "tokenize_tc_run: bad shape");
+  if (B == 0) return RQB_OK;
+  RQB_CHECK_ARG(x && state && ids, "tokenize_tc_run: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const char* base = reinterpret_cast<const char*>(state);
+  TcParams p{};
+  p.x = x; p.ldx = ldx; p.B = B; p.D = D; p.L = L; p.nkc = D / TC_KC;
+  p.ntiles = (B + TC_BM - 1) / TC_BM;
+  p.hdr = reinterpret_cast<const TcHeader*>(base);
+  p.cc = reinterpret_cast<const float*>(base + tc_off_cc(L));
+  p.gram = reinterpret_cast<const float*>(base + tc_off_gram(L));
+  p.cb = reinterpret_cast<const float* const*>(base + tc_off_cbptr(L));
+  p.blob = reinterpret_cast<const unsigned char*>(base + tc_off_blob(L));
+  p.ids = ids; p.stats = stats; p.sx = 1.0f;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    RQB_CUDA(cudaGetDevice(&dev));
+    RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const size_t smem = (size_t)TC_MAX_KC * TC_ACHUNK_BYTES + TC_BSTAGES * TC_BSTAGE_BYTES + sizeof(TcSmemMisc);
+  RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
+  rq_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
 }

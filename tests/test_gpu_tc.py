@@ -1,0 +1,99 @@
+"""GPU parity of the tcgen05 tokeniser (fp16 candidate filter + exact fp32 re-rank) against the oracle, the
+reference-generated fixtures and the exact CUDA-core kernel.  `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+import inputs as I
+from oracle import rq_oracle as O
+from parity import assert_ids_match, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rq_vae_recommender_b200 import ops as _ops
+    return _ops
+
+
+def run_tc(ops, x, cbs):
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ids = ops.rq_tokenize_tc(dev(x), [dev(c) for c in cbs], stats=stats)
+    torch.cuda.synchronize()
+    return ids.cpu().numpy(), stats.cpu().numpy()
+
+
+def test_tc_supported(ops):
+    assert ops.tc_supported(768, 256, 3) and ops.tc_supported(64, 256, 1)
+    assert not ops.tc_supported(32, 256, 3) and not ops.tc_supported(768, 128, 3) and not ops.tc_supported(800, 256, 3)
+
+
+def test_tc_ns_vs_reference(ops):
+    g = load_golden("rq_ns2048")
+    n, D, K, L = (int(v) for v in g["shape"])
+    x, cbs = I.rq_problem(n, D, K, L, seed=1234)
+    ids, stats = run_tc(ops, x, cbs)
+    n_tie = assert_ids_match(ids, g["eval_ids"], x, cbs, "tc/ns2048")
+    assert n_tie <= 2
+    assert stats[0] < 0.2 * n * L, stats      # the filter decides most rows alone
+
+
+@pytest.mark.parametrize("B,D,L", [(1, 768, 3), (100, 768, 3), (128, 768, 1), (129, 768, 2), (1000, 64, 3),
+                                    (777, 128, 4), (5000, 256, 3), (4096, 512, 2), (20000, 768, 3)])
+def test_tc_vs_oracle_shapes(ops, B, D, L):
+    K = 256
+    x, cbs = I.rq_problem(max(B, 1024), D, K, L, seed=B + D + L)
+    x = x[:B]
+    ids, stats = run_tc(ops, x, cbs)
+    ref = O.rq_tokenize(x, cbs)
+    n_tie = assert_ids_match(ids, ref, x, cbs, f"tc B={B} D={D} L={L}")
+    assert n_tie <= max(2, B // 2000)
+    exact = ops.rq_tokenize(dev(x), [dev(c) for c in cbs]).cpu().numpy()
+    assert (ids != exact).any(1).sum() <= max(2, B // 2000)
+
+
+def test_tc_scaled_and_extreme_inputs(ops):
+    """Rows at very different scales, rows that overflow fp16, exact duplicates of codes, zero rows."""
+    D, K, L = 768, 256, 3
+    x, cbs = I.rq_problem(2048, D, K, L, seed=99)
+    x = x[:512].copy()
+    x[0:64] *= 1e-3
+    x[64:128] *= 37.0
+    x[128:132] *= 1e6            # fp16 overflow -> every code re-ranked exactly
+    x[132:136] = 0.0
+    x[136:140] = cbs[0][10:14]   # exact hits
+    x[140, 5] = np.inf
+    ids, stats = run_tc(ops, x[:140], cbs)
+    ref = O.rq_tokenize(x[:140], cbs)
+    assert_ids_match(ids, ref, x[:140], cbs, "tc/extreme")
+    assert (ids[136:140, 0] == np.arange(10, 14)).all()
+    ids2, _ = run_tc(ops, x[:141], cbs)          # a non-finite row must not disturb its neighbours
+    assert (ids2[:140] == ids).all()
+
+
+def test_tc_exact_ties_pick_first_index(ops):
+    D, K, L = 128, 256, 2
+    x, cbs = I.rq_problem(1024, D, K, L, seed=5)
+    cbs[0][200] = cbs[0][17]
+    cbs[0][90] = cbs[0][17]
+    x = np.repeat(cbs[0][17:18], 256, axis=0) + 1e-4 * I.randn(4, 256, D)
+    ids, stats = run_tc(ops, x, cbs)
+    assert (ids[:, 0] == 17).all()
+    assert stats[0] >= 256          # every row needed the exact re-rank at level 0
+
+
+def test_tc_strided_rows_and_state_reuse(ops):
+    D, K, L = 768, 256, 3
+    x, cbs = I.rq_problem(1024, D, K, L, seed=21)
+    state = ops.TcState([dev(c) for c in cbs])
+    big = torch.zeros(1024, 1024, device="cuda")
+    big[:, 128:128 + D] = dev(x)
+    a = ops.rq_tokenize_tc(big[:, 128:128 + D], state=state).cpu().numpy()
+    b = ops.rq_tokenize_tc(dev(x), state=state).cpu().numpy()
+    assert np.array_equal(a, b)
+    assert_ids_match(b, O.rq_tokenize(x, cbs), x, cbs)
