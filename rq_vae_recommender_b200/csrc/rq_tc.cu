@@ -36,7 +36,7 @@ extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float a
 #define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
 #define TC_NCONV_WARPS 8
 #define TC_NEPI_WARPS 4
-#define TC_THREADS ((2 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)
+#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 8 converters | 4 epilogue
 #define TC_Z 6.0f         // margin multiplier on the statistical fp16 rounding bound
 
 struct TcLevelConst {
@@ -196,8 +196,8 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// 32 consecutive fp32 columns of this thread's TMEM lane (row); asynchronous until tc_ld_wait()
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -206,12 +206,9 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B: 8 rows x 128 B)
@@ -255,7 +252,40 @@ struct TcSmemMisc {
   uint32_t tmem_base;
   uint32_t pad;
   float2 rowinfo[TC_BM];  // (sum x^4, sum x^2) of the tile being scored
+  float cc[TC_K];         // ||c||^2 of the level being scored (all epilogue threads read the same values)
 };
+
+template <int N> __device__ __forceinline__ void tc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void tc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void tc_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// one 32-column slice of the score row: approx dist = cc - 2 (S*inv - corr); top-3 tracking (values) + top-2 indices
+__device__ __forceinline__ void tc_score32(const uint32_t (&sr)[32], const float4* corr, const float* cc_s, int col0,
+                                           float inv, float& m1, float& m2, float& m3, int& i1, int& i2) {
+#pragma unroll
+  for (int v4 = 0; v4 < 8; ++v4) {
+    const float4 cc4 = *reinterpret_cast<const float4*>(cc_s + col0 + v4 * 4);
+    const float4 g = corr[v4];
+    const float av[4] = {cc4.x - 2.f * (__uint_as_float(sr[v4 * 4 + 0]) * inv - g.x),
+                         cc4.y - 2.f * (__uint_as_float(sr[v4 * 4 + 1]) * inv - g.y),
+                         cc4.z - 2.f * (__uint_as_float(sr[v4 * 4 + 2]) * inv - g.z),
+                         cc4.w - 2.f * (__uint_as_float(sr[v4 * 4 + 3]) * inv - g.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // branch-free top-3 insertion (values) / top-2 (indices); strict '<' keeps the first index on ties
+      const float a = av[e];
+      const int k = col0 + v4 * 4 + e;
+      const bool lt1 = a < m1, lt2 = a < m2;
+      const float hi1 = fmaxf(m1, a), nm1 = fminf(m1, a);
+      const float hi2 = fmaxf(m2, hi1), nm2 = fminf(m2, hi1);
+      m3 = fminf(m3, hi2);
+      i2 = lt1 ? i1 : (lt2 ? k : i2);
+      i1 = lt1 ? k : i1;
+      m1 = nm1;
+      m2 = nm2;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
@@ -280,9 +310,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   tc_fence_after();
   const uint32_t tmem = ms->tmem_base;
 
-  if (warp == 0) {
-    // ============================================================== B producer
-    if (lane == 0) {
+  if (warp < 4) {
+    // ============================================================== warpgroup 0: B producer (warp 0), MMA issuer (warp 1)
+    tc_setmaxnreg_dec<40>();
+    if (warp == 0 && lane == 0) {
       uint32_t s = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
         for (int l = 0; l < L; ++l)
@@ -294,10 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               bulk_g2s(sB + st * TC_BSTAGE_BYTES, p.blob + (size_t)((l * 2 + h) * nkc + kc) * TC_BSTAGE_BYTES,
                        TC_BSTAGE_BYTES, &ms->b_full[st]);
             }
-    }
-  } else if (warp == 1) {
-    // ============================================================== MMA issuer
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = tc_idesc(128, 128);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t s = 0, g = 0, it = 0;
@@ -325,9 +353,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           tc_commit(&ms->t_full[buf]);
         }
     }
-  } else if (warp < 2 + TC_NCONV_WARPS) {
-    // ============================================================== converters: x fp32 -> fp16 swizzled A chunks
-    const int cw = warp - 2;                 // rows 16*cw .. 16*cw+15
+  } else if (warp < 4 + TC_NCONV_WARPS) {
+    // ============================================================== warpgroups 1-2: x fp32 -> fp16 swizzled A chunks
+    tc_setmaxnreg_dec<104>();
+    const int cw = warp - 4;                 // rows 16*cw .. 16*cw+15
     const int sub = lane >> 4, q = lane & 15;  // lane -> (row parity, float4 index inside the 64-float chunk row)
     const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
     uint32_t it = 0;
@@ -355,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = v[i];
         if (kc + 1 < nkc) load_chunk(kc + 1);          // prefetch the next chunk while this one is converted
-        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);      // the last level of the previous tile released this chunk
+        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
         unsigned char* dst = sA + kc * TC_ACHUNK_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -392,12 +421,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       }
     }
   } else {
-    // ============================================================== epilogue: scores -> candidates -> exact re-rank -> ids
-    const int ew = warp - (2 + TC_NCONV_WARPS);
+    // ============================================================== warpgroup 3: scores -> candidates -> exact re-rank -> ids
+    tc_setmaxnreg_inc<232>();
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
     const int r_local = quarter * 32 + lane;
+    const int et = r_local;                             // 0..127 index among the epilogue threads
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    (void)ew;
     uint32_t g = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row = tile * TC_BM + r_local;
@@ -406,15 +435,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       float x4s = 0.f, x2s = 0.f;
       for (int l = 0; l < L; ++l, ++g) {
         const uint32_t buf = g & 1, u = g >> 1;
+        const float* ccl = p.cc + l * TC_K;
+        const float cc_a = __ldg(ccl + et), cc_b = __ldg(ccl + et + 128);   // in flight while we wait for the MMAs
+        const TcLevelConst lc = p.hdr->lv[l];
         mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
         tc_fence_after();
+        tc_epi_bar();                       // every epilogue thread is done with the previous level's cc
+        ms->cc[et] = cc_a;
+        ms->cc[et + 128] = cc_b;
         if (l == 0) {
           const float2 ri = ms->rowinfo[r_local];
           x4s = ri.x; x2s = ri.y;
           mbar_arrive(&ms->rowinfo_free);
         }
-        // ---- margin (see DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|
-        const TcLevelConst lc = p.hdr->lv[l];
+        tc_epi_bar();
+        // ---- margin (DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|
         const float x2n = sqrtf(x2s);
         const float sig = 4.8828125e-4f * 0.81649658f * sqrtf(sqrtf(x4s) * lc.c4max);          // u=2^-11, sqrt(2/3)
         const float flo = 2.98023224e-8f * (lc.c1max / p.sx + sqrtf((float)p.D) * x2n / lc.sc);  // fp16 subnormal floor
@@ -422,56 +457,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float eps = TC_Z * sig + flo + acc + lc.gerr;
         const float margin = 4.f * eps;
         const float inv = 1.f / (p.sx * lc.sc);
-        const float* ccl = p.cc + l * TC_K;
         const uint32_t tcol = tmem + lane_addr + buf * 256;
 
-        float m1 = INFINITY, m2 = INFINITY;
-        int i1 = 0;
+        // Gram rows of the codes already chosen at levels j < l (two tables with all loads of a 64-column batch in
+        // flight at once; L > 3 adds the rest serially)
+        const float* grow0 = p.gram;
+        const float* grow1 = p.gram;
+        if (l >= 1) grow0 = p.gram + ((size_t)(l * (l - 1) / 2 + 0) * TC_K + (size_t)(idpack & 0xff)) * TC_K;
+        if (l >= 2) grow1 = p.gram + ((size_t)(l * (l - 1) / 2 + 1) * TC_K + (size_t)((idpack >> 8) & 0xff)) * TC_K;
+
+        float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+        int i1 = 0, i2 = 0;
+#pragma unroll 1
+        for (int b64 = 0; b64 < 4; ++b64) {
+          const int c0 = b64 * 64;
+          float4 ga[16], gb[16];
+          uint32_t sr[32];
+          tc_ld32_issue(tcol + c0, sr);
+          if (valid && l >= 1) {
+#pragma unroll
+            for (int v4 = 0; v4 < 16; ++v4) ga[v4] = __ldg(reinterpret_cast<const float4*>(grow0 + c0) + v4);
+          } else {
+#pragma unroll
+            for (int v4 = 0; v4 < 16; ++v4) ga[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (valid && l >= 2) {
+#pragma unroll
+            for (int v4 = 0; v4 < 16; ++v4) gb[v4] = __ldg(reinterpret_cast<const float4*>(grow1 + c0) + v4);
+#pragma unroll
+            for (int v4 = 0; v4 < 16; ++v4) { ga[v4].x += gb[v4].x; ga[v4].y += gb[v4].y; ga[v4].z += gb[v4].z; ga[v4].w += gb[v4].w; }
+          }
+          for (int j = 2; j < l; ++j) {   // L > 3 only
+            const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + c0;
+            if (valid) {
+#pragma unroll
+              for (int v4 = 0; v4 < 16; ++v4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(gj) + v4);
+                ga[v4].x += t.x; ga[v4].y += t.y; ga[v4].z += t.z; ga[v4].w += t.w;
+              }
+            }
+          }
+          tc_ld_wait();
+          if (valid) tc_score32(sr, ga, ms->cc, c0, inv, m1, m2, m3, i1, i2);
+          tc_ld32_issue(tcol + c0 + 32, sr);
+          tc_ld_wait();
+          if (valid) tc_score32(sr, ga + 8, ms->cc, c0 + 32, inv, m1, m2, m3, i1, i2);
+        }
+        const float thr = m1 + margin;
+        const bool flagged = valid && !(m2 > thr);          // >= 2 candidates (NaN/inf margins land here too)
+        const bool many = flagged && !(m3 > thr);           // >= 3 candidates: rare, needs the full candidate mask
+        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+        const uint32_t mn = __ballot_sync(0xffffffffu, many);
         uint32_t mask[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) mask[c] = 0;
-
-        auto scan = [&](bool second) {
+        if (mn) {
+          // second pass over the scores (warp-uniform branch): exact candidate bitmask for the `many` rows
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
-            float sv[32];
-            tc_ld32(tcol + c * 32, sv);
+            uint32_t sr[32];
+            tc_ld32_issue(tcol + c * 32, sr);
+            tc_ld_wait();
             uint32_t mw = 0;
-            if (valid) {
+            if (many) {
+#pragma unroll 1
+              for (int e = 0; e < 32; ++e) {
+                const int k = c * 32 + e;
+                float corr = 0.f;
+                for (int j = 0; j < l; ++j)
+                  corr += __ldg(p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + k);
+                float sv = 0.f;
 #pragma unroll
-              for (int v4 = 0; v4 < 8; ++v4) {
-                const float4 cc4 = __ldg(reinterpret_cast<const float4*>(ccl + c * 32 + v4 * 4));
-                float4 corr = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int j = 0; j < l; ++j) {
-                  const int idj = (int)((idpack >> (8 * j)) & 0xff);
-                  const float4 gj = __ldg(reinterpret_cast<const float4*>(
-                      p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + idj) * TC_K + c * 32 + v4 * 4));
-                  corr.x += gj.x; corr.y += gj.y; corr.z += gj.z; corr.w += gj.w;
-                }
-                const float a0 = cc4.x - 2.f * (sv[v4 * 4 + 0] * inv - corr.x);
-                const float a1 = cc4.y - 2.f * (sv[v4 * 4 + 1] * inv - corr.y);
-                const float a2 = cc4.z - 2.f * (sv[v4 * 4 + 2] * inv - corr.z);
-                const float a3 = cc4.w - 2.f * (sv[v4 * 4 + 3] * inv - corr.w);
-                const float av[4] = {a0, a1, a2, a3};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int k = c * 32 + v4 * 4 + e;
-                  if (!second) {
-                    if (av[e] < m1) { m2 = m1; m1 = av[e]; i1 = k; }
-                    else if (av[e] < m2) { m2 = av[e]; }
-                  } else {
-                    if (!(av[e] > m1 + margin)) mw |= 1u << (v4 * 4 + e);
-                  }
-                }
+                for (int t = 0; t < 32; ++t) if (t == e) sv = __uint_as_float(sr[t]);
+                const float a = ms->cc[k] - 2.f * (sv * inv - corr);
+                if (!(a > thr)) mw |= 1u << e;
               }
             }
-            if (second) mask[c] = mw;
+            mask[c] = mw;
           }
-        };
-        scan(false);
-        bool flagged = valid && !(m2 > m1 + margin);
-        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
-        if (fl) scan(true);
+        }
         tc_fence_before();
         mbar_arrive(&ms->t_empty[buf]);     // accumulator buffer may be overwritten by level l+2
 
@@ -486,6 +550,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           const uint32_t idlo = __shfl_sync(0xffffffffu, (uint32_t)idpack, src);
           const uint32_t idhi = __shfl_sync(0xffffffffu, (uint32_t)(idpack >> 32), src);
           const uint64_t rid = ((uint64_t)idhi << 32) | idlo;
+          const int ci1 = __shfl_sync(0xffffffffu, i1, src), ci2 = __shfl_sync(0xffffffffu, i2, src);
+          const bool is_many = (mn >> src) & 1;
           float res[TC_MAX_D / 32];
           const float* xr = p.x + (int64_t)rrow * p.ldx;
 #pragma unroll
@@ -500,33 +566,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll
           for (int i = 0; i < TC_MAX_D / 32; ++i) xx = fmaf(res[i], res[i], xx);
           xx = warp_sum(xx);
+          const float* cl = p.cb[l];
           float best = INFINITY;
           int besti = 0x7fffffff;
-          const float* cl = p.cb[l];
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            uint32_t mw = __shfl_sync(0xffffffffu, mask[c], src);
-            while (mw) {
-              const int k = c * 32 + __ffs(mw) - 1;
-              mw &= mw - 1;
-              const float* ck = cl + (int64_t)k * p.D;
-              float dot = 0.f;
+          if (!is_many) {
+            // exactly two candidates: both dot products with all their loads in flight, ascending index order
+            const int ka = min(ci1, ci2), kb = max(ci1, ci2);
+            const float* pa = cl + (int64_t)ka * p.D;
+            const float* pb = cl + (int64_t)kb * p.D;
+            float da = 0.f, db = 0.f;
 #pragma unroll
-              for (int i = 0; i < TC_MAX_D / 32; ++i)
-                if (i * 32 < p.D) dot = fmaf(res[i], __ldg(ck + i * 32 + lane), dot);
-              dot = warp_sum(dot);
-              const float dist = (xx + __ldg(ccl + k)) - 2.f * dot;             // quantize.py:113-117
-              if (dist < best) { best = dist; besti = k; }
-              ++n_cand;
+            for (int i = 0; i < TC_MAX_D / 32; ++i)
+              if (i * 32 < p.D) {
+                da = fmaf(res[i], __ldg(pa + i * 32 + lane), da);
+                db = fmaf(res[i], __ldg(pb + i * 32 + lane), db);
+              }
+            da = warp_sum(da);
+            db = warp_sum(db);
+            const float dist_a = (xx + ms->cc[ka]) - 2.f * da;                  // quantize.py:113-117
+            const float dist_b = (xx + ms->cc[kb]) - 2.f * db;
+            best = dist_a; besti = ka;
+            if (dist_b < best) { best = dist_b; besti = kb; }
+            if (!(dist_a == dist_a)) besti = (dist_b == dist_b) ? kb : ci1;     // NaN distances: keep something valid
+            n_cand += 2;
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint32_t mw = __shfl_sync(0xffffffffu, mask[c], src);
+              while (mw) {
+                const int k = c * 32 + __ffs(mw) - 1;
+                mw &= mw - 1;
+                const float* ck = cl + (int64_t)k * p.D;
+                float dot = 0.f;
+#pragma unroll
+                for (int i = 0; i < TC_MAX_D / 32; ++i)
+                  if (i * 32 < p.D) dot = fmaf(res[i], __ldg(ck + i * 32 + lane), dot);
+                dot = warp_sum(dot);
+                const float dist = (xx + ms->cc[k]) - 2.f * dot;
+                if (dist < best) { best = dist; besti = k; }
+                ++n_cand;
+              }
             }
+            if (besti > 255) besti = ci1;   // all-NaN row: keep the filter's pick
           }
-          if (besti > 255) besti = __shfl_sync(0xffffffffu, i1, src);  // all-NaN row: keep the filter's pick
           if (lane == src) my_id = besti;
         }
         if (p.stats && lane == 0 && fl) {
           atomicAdd(p.stats + 0, __popc(fl));
           atomicAdd(p.stats + 1, n_cand);
-          atomicAdd(p.stats + 2, 32);
+          atomicAdd(p.stats + 2, __popc(mn));
         }
         idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
