@@ -35,8 +35,8 @@ extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float a
 #define TC_BSTAGE_BYTES (128 * TC_KC * 2)   // 128 codes x 64 k x fp16 = 16 KB
 #define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
 #define TC_NCONV_WARPS 8
-#define TC_NEPI_WARPS 4
-#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 8 converters | 4 epilogue
+#define TC_NEPI_WARPS 8
+#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 8 converters | 8 epilogue (2 per TMEM lane quarter)
 #define TC_Z 6.0f         // margin multiplier on the statistical fp16 rounding bound
 
 struct TcLevelConst {
@@ -57,7 +57,8 @@ struct TcHeader {
 };
 
 static size_t tc_off_cc(int L) { return rqb_round_up(sizeof(TcHeader), 256); }
-static size_t tc_off_gram(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
+static size_t tc_off_hcc(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
+static size_t tc_off_gram(int L) { return tc_off_hcc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
 static size_t tc_off_cbptr(int L) { return tc_off_gram(L) + (size_t)(L * (L - 1) / 2) * TC_K * TC_K * 4; }
 static size_t tc_off_blob(int L) { return rqb_round_up(tc_off_cbptr(L) + RQB_MAX_LEVELS * 8, 1024); }
 
@@ -134,6 +135,19 @@ __global__ void tc_prep_blob_kernel(const float* const* cbs, int D, const TcHead
   }
 }
 
+// hcc[l][k] = cc_l[k] / 2;  G_{0,l}[i][k] += cc_l[k] / 2  (l >= 1): the epilogue then scores with ONE table sum,
+// half-distance h[k] = T[k] - S[k]*inv,  T = cc/2 + sum_j G_{j,l}[id_j]  (argmin-equivalent to quantize.py:113-117)
+__global__ void tc_prep_fold_kernel(const float* cc, float* hcc, float* gram, int L) {
+  const int l = blockIdx.y;
+  const int k = threadIdx.x;   // 256 threads
+  const float h = 0.5f * cc[l * TC_K + k];
+  if (blockIdx.x == 0) hcc[l * TC_K + k] = h;
+  if (l >= 1) {
+    float* g = gram + (size_t)(l * (l - 1) / 2) * TC_K * TC_K;   // table (j = 0, l)
+    for (int i = blockIdx.x; i < TC_K; i += gridDim.x) g[(size_t)i * TC_K + k] += h;
+  }
+}
+
 extern "C" int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, int K, int L, void* state,
                                           size_t state_bytes, void* stream) {
   if (!rqb200_tokenize_tc_supported(D, K, L)) {
@@ -166,6 +180,9 @@ extern "C" int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, 
       int rc = rqb200_sgemm(0, 1, TC_K, TC_K, D, 1.f, codebooks[j], D, codebooks[l], D, 0.f, g, TC_K, 0, nullptr, 0, stream);
       if (rc) return rc;
     }
+  float* hcc = reinterpret_cast<float*>(base + tc_off_hcc(L));
+  tc_prep_fold_kernel<<<dim3(32, L), TC_K, 0, st>>>(cc, hcc, gram, L);
+  RQB_LAUNCH_CHECK();
   return RQB_OK;
 }
 
@@ -236,6 +253,7 @@ struct TcParams {
   int B, D, L, nkc, ntiles;
   const TcHeader* hdr;
   const float* cc;      // [L][256]
+  const float* hcc;     // [L][256]  cc / 2
   const float* gram;    // [L(L-1)/2][256][256]
   const float* const* cb;  // device array of L fp32 codebook pointers (exact re-rank)
   const unsigned char* blob;
@@ -244,47 +262,42 @@ struct TcParams {
   float sx;             // power-of-two scale applied to x before fp16 conversion
 };
 
+struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
+
 struct TcSmemMisc {
   uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
   uint64_t b_full[TC_BSTAGES], b_empty[TC_BSTAGES];
-  uint64_t t_full[2], t_empty[2];
+  uint64_t t_full[2][2];          // [accumulator buffer][column half]
+  uint64_t t_empty[2];
   uint64_t rowinfo_free;
   uint32_t tmem_base;
   uint32_t pad;
-  float2 rowinfo[TC_BM];  // (sum x^4, sum x^2) of the tile being scored
-  float cc[TC_K];         // ||c||^2 of the level being scored (all epilogue threads read the same values)
+  uint32_t rowinfo[TC_BM];        // bf16x2 (rounded up): sum x^4 | sum x^2 of the tile being scored
+  TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
 };
 
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void tc_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tc_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tc_pair_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
 
-// one 32-column slice of the score row: approx dist = cc - 2 (S*inv - corr); top-3 tracking (values) + top-2 indices
-__device__ __forceinline__ void tc_score32(const uint32_t (&sr)[32], const float4* corr, const float* cc_s, int col0,
-                                           float inv, float& m1, float& m2, float& m3, int& i1, int& i2) {
-#pragma unroll
-  for (int v4 = 0; v4 < 8; ++v4) {
-    const float4 cc4 = *reinterpret_cast<const float4*>(cc_s + col0 + v4 * 4);
-    const float4 g = corr[v4];
-    const float av[4] = {cc4.x - 2.f * (__uint_as_float(sr[v4 * 4 + 0]) * inv - g.x),
-                         cc4.y - 2.f * (__uint_as_float(sr[v4 * 4 + 1]) * inv - g.y),
-                         cc4.z - 2.f * (__uint_as_float(sr[v4 * 4 + 2]) * inv - g.z),
-                         cc4.w - 2.f * (__uint_as_float(sr[v4 * 4 + 3]) * inv - g.w)};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      // branch-free top-3 insertion (values) / top-2 (indices); strict '<' keeps the first index on ties
-      const float a = av[e];
-      const int k = col0 + v4 * 4 + e;
-      const bool lt1 = a < m1, lt2 = a < m2;
-      const float hi1 = fmaxf(m1, a), nm1 = fminf(m1, a);
-      const float hi2 = fmaxf(m2, hi1), nm2 = fminf(m2, hi1);
-      m3 = fminf(m3, hi2);
-      i2 = lt1 ? i1 : (lt2 ? k : i2);
-      i1 = lt1 ? k : i1;
-      m1 = nm1;
-      m2 = nm2;
-    }
-  }
+__device__ __forceinline__ uint32_t tc_bf16_up(float v) {   // bf16 bits of the smallest bf16 >= v (v >= 0, inf/nan kept)
+  uint32_t b = __float_as_uint(v);
+  if ((b & 0x7f800000u) != 0x7f800000u && (b & 0xffffu)) b += 0x10000u;
+  return b >> 16;
+}
+
+// branch-free insertion of (a, k) into the sorted top-3 values / top-2 indices; strict '<' keeps the earlier index
+__device__ __forceinline__ void tc_insert(float a, int k, float& m1, float& m2, float& m3, int& i1, int& i2) {
+  const bool lt1 = a < m1, lt2 = a < m2;
+  m3 = fminf(m3, fmaxf(m2, a));
+  m2 = fminf(m2, fmaxf(m1, a));
+  m1 = fminf(m1, a);
+  i2 = lt1 ? i1 : (lt2 ? k : i2);
+  i1 = lt1 ? k : i1;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
@@ -300,7 +313,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
     for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], TC_NCONV_WARPS * 32); mbar_init(&ms->a_empty[i], 1); }
     for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], TC_NEPI_WARPS * 32); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ms->t_full[i][0], 1);
+      mbar_init(&ms->t_full[i][1], 1);
+      mbar_init(&ms->t_empty[i], TC_NEPI_WARPS * 32);
+    }
     mbar_init(&ms->rowinfo_free, TC_NEPI_WARPS * 32);
     fence_mbar_init();
   }
@@ -312,7 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
   if (warp < 4) {
     // ============================================================== warpgroup 0: B producer (warp 0), MMA issuer (warp 1)
-    tc_setmaxnreg_dec<40>();
+    // register budget (per-CTA pool = 640 threads x 96 at launch = 61440): 128x32 + 256x96 + 256x128 = 61440
+    tc_setmaxnreg_dec<32>();
     if (warp == 0 && lane == 0) {
       uint32_t s = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
@@ -349,13 +367,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               tc_commit(&ms->b_empty[st]);
               if (l == L - 1 && h == 1) tc_commit(&ms->a_empty[kc]);
             }
+            tc_commit(&ms->t_full[buf][h]);   // this 128-column half of the score tile is complete
           }
-          tc_commit(&ms->t_full[buf]);
         }
     }
   } else if (warp < 4 + TC_NCONV_WARPS) {
     // ============================================================== warpgroups 1-2: x fp32 -> fp16 swizzled A chunks
-    tc_setmaxnreg_dec<104>();
     const int cw = warp - 4;                 // rows 16*cw .. 16*cw+15
     const int sub = lane >> 4, q = lane & 15;  // lane -> (row parity, float4 index inside the 64-float chunk row)
     const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
@@ -413,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], o);
               s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
             }
-            if (q == 0) ms->rowinfo[cw * 16 + 2 * i + sub] = make_float2(s4[i], s2[i]);
+            if (q == 0) ms->rowinfo[cw * 16 + 2 * i + sub] = (tc_bf16_up(s4[i]) << 16) | tc_bf16_up(s2[i]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -421,12 +438,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       }
     }
   } else {
-    // ============================================================== warpgroup 3: scores -> candidates -> exact re-rank -> ids
-    tc_setmaxnreg_inc<232>();
+    // ============================================================== warpgroups 3-4: scores -> candidates -> exact re-rank -> ids
+    // two warps per TMEM lane quarter: `half` 0 scans columns [0,128) and owns merge / re-rank / ids, half 1 scans [128,256)
+    tc_setmaxnreg_inc<128>();
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = (warp - (4 + TC_NCONV_WARPS)) >> 2;
     const int r_local = quarter * 32 + lane;
-    const int et = r_local;                             // 0..127 index among the epilogue threads
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int bar_x = 2 + quarter;      // half 1 -> half 0: exch[] written
+    const int bar_i = 6 + quarter;      // half 0 -> half 1: the level's id is final (written into exch[].idx)
     uint32_t g = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row = tile * TC_BM + r_local;
@@ -435,73 +455,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       float x4s = 0.f, x2s = 0.f;
       for (int l = 0; l < L; ++l, ++g) {
         const uint32_t buf = g & 1, u = g >> 1;
-        const float* ccl = p.cc + l * TC_K;
-        const float cc_a = __ldg(ccl + et), cc_b = __ldg(ccl + et + 128);   // in flight while we wait for the MMAs
         const TcLevelConst lc = p.hdr->lv[l];
-        mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
+        // T rows: hcc (level 0, shared by all rows) or the Gram rows of the codes chosen at levels j < l (cc/2 folded in j=0)
+        const float* trow0 = p.hcc + half * 128;
+        const float* trow1 = trow0;
+        if (l >= 1) trow0 = p.gram + ((size_t)(l * (l - 1) / 2 + 0) * TC_K + (size_t)(idpack & 0xff)) * TC_K + half * 128;
+        if (l >= 2) trow1 = p.gram + ((size_t)(l * (l - 1) / 2 + 1) * TC_K + (size_t)((idpack >> 8) & 0xff)) * TC_K + half * 128;
+        mbar_wait_guarded(&ms->t_full[buf][half], u & 1, 7);
         tc_fence_after();
-        tc_epi_bar();                       // every epilogue thread is done with the previous level's cc
-        ms->cc[et] = cc_a;
-        ms->cc[et + 128] = cc_b;
         if (l == 0) {
-          const float2 ri = ms->rowinfo[r_local];
-          x4s = ri.x; x2s = ri.y;
+          const uint32_t ri = ms->rowinfo[r_local];
+          x4s = __uint_as_float(ri & 0xffff0000u);
+          x2s = __uint_as_float(ri << 16);
           mbar_arrive(&ms->rowinfo_free);
         }
-        tc_epi_bar();
-        // ---- margin (DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|
+        // ---- margin (DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|; scores are half-distances
         const float x2n = sqrtf(x2s);
         const float sig = 4.8828125e-4f * 0.81649658f * sqrtf(sqrtf(x4s) * lc.c4max);          // u=2^-11, sqrt(2/3)
         const float flo = 2.98023224e-8f * (lc.c1max / p.sx + sqrtf((float)p.D) * x2n / lc.sc);  // fp16 subnormal floor
         const float acc = 7.62939453e-6f * x2n * lc.c2max;                                      // 64 * 2^-23 accumulate
         const float eps = TC_Z * sig + flo + acc + lc.gerr;
-        const float margin = 4.f * eps;
-        const float inv = 1.f / (p.sx * lc.sc);
-        const uint32_t tcol = tmem + lane_addr + buf * 256;
-
-        // Gram rows of the codes already chosen at levels j < l (two tables with all loads of a 64-column batch in
-        // flight at once; L > 3 adds the rest serially)
-        const float* grow0 = p.gram;
-        const float* grow1 = p.gram;
-        if (l >= 1) grow0 = p.gram + ((size_t)(l * (l - 1) / 2 + 0) * TC_K + (size_t)(idpack & 0xff)) * TC_K;
-        if (l >= 2) grow1 = p.gram + ((size_t)(l * (l - 1) / 2 + 1) * TC_K + (size_t)((idpack >> 8) & 0xff)) * TC_K;
+        const float margin = 2.f * eps;
+        const float ninv = -1.f / (p.sx * lc.sc);
+        const uint32_t tcol = tmem + lane_addr + buf * 256 + half * 128;
 
         float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
         int i1 = 0, i2 = 0;
 #pragma unroll 1
-        for (int b64 = 0; b64 < 4; ++b64) {
-          const int c0 = b64 * 64;
-          float4 ga[16], gb[16];
+        for (int c = 0; c < 4; ++c) {
           uint32_t sr[32];
-          tc_ld32_issue(tcol + c0, sr);
-          if (valid && l >= 1) {
+          tc_ld32_issue(tcol + c * 32, sr);
+          float4 ta[8], tb[8];
+          if (valid) {
 #pragma unroll
-            for (int v4 = 0; v4 < 16; ++v4) ga[v4] = __ldg(reinterpret_cast<const float4*>(grow0 + c0) + v4);
+            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = __ldg(reinterpret_cast<const float4*>(trow0 + c * 32) + v4);
           } else {
 #pragma unroll
-            for (int v4 = 0; v4 < 16; ++v4) ga[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (valid && l >= 2) {
 #pragma unroll
-            for (int v4 = 0; v4 < 16; ++v4) gb[v4] = __ldg(reinterpret_cast<const float4*>(grow1 + c0) + v4);
+            for (int v4 = 0; v4 < 8; ++v4) tb[v4] = __ldg(reinterpret_cast<const float4*>(trow1 + c * 32) + v4);
 #pragma unroll
-            for (int v4 = 0; v4 < 16; ++v4) { ga[v4].x += gb[v4].x; ga[v4].y += gb[v4].y; ga[v4].z += gb[v4].z; ga[v4].w += gb[v4].w; }
+            for (int v4 = 0; v4 < 8; ++v4) { ta[v4].x += tb[v4].x; ta[v4].y += tb[v4].y; ta[v4].z += tb[v4].z; ta[v4].w += tb[v4].w; }
           }
           for (int j = 2; j < l; ++j) {   // L > 3 only
-            const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + c0;
+            const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + half * 128 + c * 32;
             if (valid) {
 #pragma unroll
-              for (int v4 = 0; v4 < 16; ++v4) {
+              for (int v4 = 0; v4 < 8; ++v4) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(gj) + v4);
-                ga[v4].x += t.x; ga[v4].y += t.y; ga[v4].z += t.z; ga[v4].w += t.w;
+                ta[v4].x += t.x; ta[v4].y += t.y; ta[v4].z += t.z; ta[v4].w += t.w;
               }
             }
           }
           tc_ld_wait();
-          if (valid) tc_score32(sr, ga, ms->cc, c0, inv, m1, m2, m3, i1, i2);
-          tc_ld32_issue(tcol + c0 + 32, sr);
-          tc_ld_wait();
-          if (valid) tc_score32(sr, ga + 8, ms->cc, c0 + 32, inv, m1, m2, m3, i1, i2);
+          if (valid) {
+            // chunk-local top-3 with immediate indices, then one merge into the running top-3
+            float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
+            int j1 = 0, j2 = 0;
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4) {
+              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 0]), ninv, ta[v4].x), v4 * 4 + 0, q1, q2, q3, j1, j2);
+              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 1]), ninv, ta[v4].y), v4 * 4 + 1, q1, q2, q3, j1, j2);
+              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 2]), ninv, ta[v4].z), v4 * 4 + 2, q1, q2, q3, j1, j2);
+              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 3]), ninv, ta[v4].w), v4 * 4 + 3, q1, q2, q3, j1, j2);
+            }
+            const int kb = half * 128 + c * 32;
+            tc_insert(q1, kb + j1, m1, m2, m3, i1, i2);
+            tc_insert(q2, kb + j2, m1, m2, m3, i1, i2);
+            m3 = fminf(m3, fmaxf(m2, q3)); // q3 >= q2: it can only displace m3
+          }
+        }
+
+        if (half == 1) {
+          // ---- hand the top-3 of columns [128,256) to the half-0 warp of this lane quarter, then wait for the final id
+          TcExch e; e.m1 = m1; e.m2 = m2; e.m3 = m3; e.idx = (uint32_t)i1 | ((uint32_t)i2 << 8);
+          ms->exch[r_local] = e;
+          tc_fence_before();
+          mbar_arrive(&ms->t_empty[buf]);
+          tc_pair_arrive(bar_x);
+          tc_pair_sync(bar_i);
+          idpack |= (uint64_t)(ms->exch[r_local].idx & 0xff) << (8 * l);
+          continue;
+        }
+
+        tc_pair_sync(bar_x);
+        {
+          const TcExch e = ms->exch[r_local];
+          tc_insert(e.m1, (int)(e.idx & 0xff), m1, m2, m3, i1, i2);
+          tc_insert(e.m2, (int)((e.idx >> 8) & 0xff), m1, m2, m3, i1, i2);
+          m3 = fminf(m3, fmaxf(m2, e.m3));
         }
         const float thr = m1 + margin;
         const bool flagged = valid && !(m2 > thr);          // >= 2 candidates (NaN/inf margins land here too)
@@ -512,25 +556,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) mask[c] = 0;
         if (mn) {
-          // second pass over the scores (warp-uniform branch): exact candidate bitmask for the `many` rows
+          // second pass over all 256 scores (warp-uniform branch): exact candidate bitmask for the `many` rows
+          const uint32_t tall = tmem + lane_addr + buf * 256;
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
             uint32_t sr[32];
-            tc_ld32_issue(tcol + c * 32, sr);
+            tc_ld32_issue(tall + c * 32, sr);
             tc_ld_wait();
             uint32_t mw = 0;
             if (many) {
 #pragma unroll 1
               for (int e = 0; e < 32; ++e) {
                 const int k = c * 32 + e;
-                float corr = 0.f;
+                float t = (l == 0) ? __ldg(p.hcc + k) : 0.f;
                 for (int j = 0; j < l; ++j)
-                  corr += __ldg(p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + k);
+                  t += __ldg(p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + k);
                 float sv = 0.f;
 #pragma unroll
-                for (int t = 0; t < 32; ++t) if (t == e) sv = __uint_as_float(sr[t]);
-                const float a = ms->cc[k] - 2.f * (sv * inv - corr);
-                if (!(a > thr)) mw |= 1u << e;
+                for (int tt = 0; tt < 32; ++tt) if (tt == e) sv = __uint_as_float(sr[tt]);
+                if (!(fmaf(sv, ninv, t) > thr)) mw |= 1u << e;
               }
             }
             mask[c] = mw;
@@ -541,6 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
         int my_id = i1;
         // ---- warp-cooperative exact re-rank of the flagged rows (same arithmetic as rq_simt.cu)
+        const float* ccl = p.cc + l * TC_K;
         uint32_t todo = fl;
         int n_cand = 0;
         while (todo) {
@@ -583,8 +628,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               }
             da = warp_sum(da);
             db = warp_sum(db);
-            const float dist_a = (xx + ms->cc[ka]) - 2.f * da;                  // quantize.py:113-117
-            const float dist_b = (xx + ms->cc[kb]) - 2.f * db;
+            const float dist_a = (xx + __ldg(ccl + ka)) - 2.f * da;             // quantize.py:113-117
+            const float dist_b = (xx + __ldg(ccl + kb)) - 2.f * db;
             best = dist_a; besti = ka;
             if (dist_b < best) { best = dist_b; besti = kb; }
             if (!(dist_a == dist_a)) besti = (dist_b == dist_b) ? kb : ci1;     // NaN distances: keep something valid
@@ -602,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
                 for (int i = 0; i < TC_MAX_D / 32; ++i)
                   if (i * 32 < p.D) dot = fmaf(res[i], __ldg(ck + i * 32 + lane), dot);
                 dot = warp_sum(dot);
-                const float dist = (xx + ms->cc[k]) - 2.f * dot;
+                const float dist = (xx + __ldg(ccl + k)) - 2.f * dot;
                 if (dist < best) { best = dist; besti = k; }
                 ++n_cand;
               }
@@ -617,6 +662,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           atomicAdd(p.stats + 2, __popc(mn));
         }
         idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
+        ms->exch[r_local].idx = (uint32_t)my_id;     // publish the final id of this level to the half-1 warp
+        tc_pair_arrive(bar_i);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
       }
     }
@@ -646,6 +693,7 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   p.ntiles = (B + TC_BM - 1) / TC_BM;
   p.hdr = reinterpret_cast<const TcHeader*>(base);
   p.cc = reinterpret_cast<const float*>(base + tc_off_cc(L));
+  p.hcc = reinterpret_cast<const float*>(base + tc_off_hcc(L));
   p.gram = reinterpret_cast<const float*>(base + tc_off_gram(L));
   p.cb = reinterpret_cast<const float* const*>(base + tc_off_cbptr(L));
   p.blob = reinterpret_cast<const unsigned char*>(base + tc_off_blob(L));
