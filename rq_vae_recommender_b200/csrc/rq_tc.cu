@@ -276,6 +276,13 @@ struct TcSmemMisc {
   TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
 };
 
+// optional cycle accounting: when stats[3] != 0 the caller passed >= 64 ints; 64-bit accumulators start at stats[8]
+__device__ __forceinline__ void tc_trace_add(int* stats, int slot, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(stats + 8) + slot, (unsigned long long)v);
+}
+#define TC_T0(var) long long var = trace ? clock64() : 0
+#define TC_ACC(acc, var) do { if (trace) { const long long n__ = clock64(); acc += n__ - var; var = n__; } } while (0)
+
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tc_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -308,6 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
+  const bool trace = p.stats != nullptr && p.stats[3] != 0;
 
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
@@ -347,17 +355,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       const uint32_t idesc = tc_idesc(128, 128);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t s = 0, g = 0, it = 0;
+      long long w_te = 0, w_af = 0, w_bf = 0, w_issue = 0;
+      TC_T0(tm);
+      const long long tm_start = tm;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it)
         for (int l = 0; l < L; ++l, ++g) {
           const uint32_t buf = g & 1, u = g >> 1;
+          TC_ACC(w_issue, tm);
           mbar_wait_guarded(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          TC_ACC(w_te, tm);
           tc_fence_after();
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem + buf * 256 + h * 128;
             for (int kc = 0; kc < nkc; ++kc, ++s) {
+              TC_ACC(w_issue, tm);
               if (l == 0 && h == 0) mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
+              TC_ACC(w_af, tm);
               const uint32_t st = s % TC_BSTAGES;
               mbar_wait_guarded(&ms->b_full[st], (s / TC_BSTAGES) & 1, 4);
+              TC_ACC(w_bf, tm);
               tc_fence_after();
               const uint64_t adesc = tc_smem_desc(a_base + kc * TC_ACHUNK_BYTES);
               const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
@@ -370,6 +386,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
             tc_commit(&ms->t_full[buf][h]);   // this 128-column half of the score tile is complete
           }
         }
+      if (trace) {
+        tc_trace_add(p.stats, 0, w_te); tc_trace_add(p.stats, 1, w_af); tc_trace_add(p.stats, 2, w_bf);
+        tc_trace_add(p.stats, 3, clock64() - tm_start); tc_trace_add(p.stats, 12, 1);
+      }
     }
   } else if (warp < 4 + TC_NCONV_WARPS) {
     // ============================================================== warpgroups 1-2: x fp32 -> fp16 swizzled A chunks
@@ -377,6 +397,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const int sub = lane >> 4, q = lane & 15;  // lane -> (row parity, float4 index inside the 64-float chunk row)
     const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
     uint32_t it = 0;
+    long long c_wait = 0, c_work = 0;
+    TC_T0(tcv);
+    const long long tcv_start = tcv;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row_base = tile * TC_BM + cw * 16;
       float s4[8], s2[8];
@@ -401,7 +424,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = v[i];
         if (kc + 1 < nkc) load_chunk(kc + 1);          // prefetch the next chunk while this one is converted
+        TC_ACC(c_work, tcv);
         mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
+        TC_ACC(c_wait, tcv);
         unsigned char* dst = sA + kc * TC_ACHUNK_BYTES;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -437,6 +462,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         mbar_arrive(&ms->a_full[kc]);
       }
     }
+    if (trace && cw == 0 && lane == 0) {
+      tc_trace_add(p.stats, 9, c_wait); tc_trace_add(p.stats, 10, clock64() - tcv_start);
+    }
   } else {
     // ============================================================== warpgroups 3-4: scores -> candidates -> exact re-rank -> ids
     // two warps per TMEM lane quarter: `half` 0 scans columns [0,128) and owns merge / re-rank / ids, half 1 scans [128,256)
@@ -448,6 +476,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const int bar_x = 2 + quarter;      // half 1 -> half 0: exch[] written
     const int bar_i = 6 + quarter;      // half 0 -> half 1: the level's id is final (written into exch[].idx)
     uint32_t g = 0, it = 0;
+    long long e_tf = 0, e_scan = 0, e_pair = 0, e_rr = 0, e_idw = 0;
+    TC_T0(te);
+    const long long te_start = te;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row = tile * TC_BM + r_local;
       const bool valid = row < p.B;
@@ -461,7 +492,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float* trow1 = trow0;
         if (l >= 1) trow0 = p.gram + ((size_t)(l * (l - 1) / 2 + 0) * TC_K + (size_t)(idpack & 0xff)) * TC_K + half * 128;
         if (l >= 2) trow1 = p.gram + ((size_t)(l * (l - 1) / 2 + 1) * TC_K + (size_t)((idpack >> 8) & 0xff)) * TC_K + half * 128;
+        TC_ACC(e_rr, te);
         mbar_wait_guarded(&ms->t_full[buf][half], u & 1, 7);
+        TC_ACC(e_tf, te);
         tc_fence_after();
         if (l == 0) {
           const uint32_t ri = ms->rowinfo[r_local];
@@ -528,6 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           }
         }
 
+        TC_ACC(e_scan, te);
         if (half == 1) {
           // ---- hand the top-3 of columns [128,256) to the half-0 warp of this lane quarter, then wait for the final id
           TcExch e; e.m1 = m1; e.m2 = m2; e.m3 = m3; e.idx = (uint32_t)i1 | ((uint32_t)i2 << 8);
@@ -536,11 +570,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           mbar_arrive(&ms->t_empty[buf]);
           tc_pair_arrive(bar_x);
           tc_pair_sync(bar_i);
+          TC_ACC(e_idw, te);
           idpack |= (uint64_t)(ms->exch[r_local].idx & 0xff) << (8 * l);
           continue;
         }
 
         tc_pair_sync(bar_x);
+        TC_ACC(e_pair, te);
         {
           const TcExch e = ms->exch[r_local];
           tc_insert(e.m1, (int)(e.idx & 0xff), m1, m2, m3, i1, i2);
@@ -666,6 +702,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         tc_pair_arrive(bar_i);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
       }
+    }
+    if (trace && quarter == 0 && lane == 0) {
+      TC_ACC(e_rr, te);
+      const int o = half ? 13 : 4;     // half 0 -> slots 4..8, half 1 -> slots 13..17
+      tc_trace_add(p.stats, o + 0, e_tf); tc_trace_add(p.stats, o + 1, e_scan); tc_trace_add(p.stats, o + 2, half ? e_idw : e_pair);
+      tc_trace_add(p.stats, o + 3, e_rr); tc_trace_add(p.stats, o + 4, clock64() - te_start);
     }
   }
 
