@@ -1,0 +1,148 @@
+"""modules/tokenizer/semids.py of the reference (:22-146) on the fused tokeniser kernels.
+
+Same class name, constructor and methods.  ``precompute_corpus_ids`` differs underneath:
+  * the corpus goes through the ids-only kernel in large batches (tcgen05 filter + exact re-rank when the shape
+    allows, else the exact CUDA-core kernel) instead of 512-row batches of full RqVae forwards;
+  * the dedup column -- the number of EARLIER corpus rows with the same id tuple, which the reference finds with an
+    O(N^2) compare against everything seen so far (semids.py:94-108, 90-97 % of its wall time) -- is the
+    rank inside a stable sort of packed tuples: identical values, O(N log N).
+"""
+from typing import List
+from typing import Optional
+
+import torch
+from torch import nn
+from torch import Tensor
+
+from .. import utils as _utils
+from ... import ops
+from ...data.schemas import SeqBatch
+from ...data.schemas import TokenizedSeqBatch
+from ..rqvae import RqVae
+
+BATCH_SIZE = 16
+eval_mode = _utils.eval_mode
+
+
+def dedup_rank(sem_ids: Tensor, codebook_size: int) -> Tensor:
+    """[N] int64: for every row, how many earlier rows carry the identical id tuple (semids.py:94-108)."""
+    N, L = sem_ids.shape
+    if N == 0:
+        return torch.zeros(0, dtype=torch.int64, device=sem_ids.device)
+    if codebook_size ** L < 2 ** 62:
+        key = sem_ids[:, 0].clone()
+        for l in range(1, L):
+            key = key * codebook_size + sem_ids[:, l]
+    else:
+        _, key = torch.unique(sem_ids, dim=0, return_inverse=True)
+    skey, order = torch.sort(key, stable=True)
+    pos = torch.arange(N, device=key.device)
+    is_start = torch.ones(N, dtype=torch.bool, device=key.device)
+    is_start[1:] = skey[1:] != skey[:-1]
+    start = torch.cummax(torch.where(is_start, pos, torch.zeros_like(pos)), dim=0).values
+    rank = torch.empty(N, dtype=torch.int64, device=key.device)
+    rank[order] = pos - start
+    return rank
+
+
+class SemanticIdTokenizer(nn.Module):
+    """
+    Tokenizes a batch of sequences of item features into a batch of sequences of semantic ids.
+    """
+
+    def __init__(
+        self,
+        input_dim: int,
+        output_dim: int,
+        hidden_dims: List[int],
+        codebook_size: int,
+        n_layers: int = 3,
+        n_cat_feats: int = 18,
+        commitment_weight: float = 0.25,
+        rqvae_weights_path: Optional[str] = None,
+        rqvae_codebook_normalize: bool = False,
+        rqvae_sim_vq: bool = False,
+    ) -> None:
+        super().__init__()
+
+        self.rq_vae = RqVae(
+            input_dim=input_dim,
+            embed_dim=output_dim,
+            hidden_dims=hidden_dims,
+            codebook_size=codebook_size,
+            codebook_kmeans_init=False,
+            codebook_normalize=rqvae_codebook_normalize,
+            codebook_sim_vq=rqvae_sim_vq,
+            n_layers=n_layers,
+            n_cat_features=n_cat_feats,
+            commitment_weight=commitment_weight,
+        )
+
+        if rqvae_weights_path is not None:
+            self.rq_vae.load_pretrained(rqvae_weights_path)
+
+        self.rq_vae.eval()
+
+        self.codebook_size = codebook_size
+        self.n_layers = n_layers
+        self.corpus_batch = 65536
+        self.reset()
+
+    def _get_hits(self, query: Tensor, key: Tensor) -> Tensor:
+        return (key.unsqueeze(0) == query.unsqueeze(1)).all(axis=-1)
+
+    def reset(self):
+        self.cached_ids = None
+
+    @property
+    def sem_ids_dim(self):
+        return self.n_layers + 1
+
+    @torch.no_grad
+    @eval_mode
+    def precompute_corpus_ids(self, movie_dataset) -> Tensor:
+        n = len(movie_dataset)
+        device = self.rq_vae.device
+        blocks = []
+        for s in range(0, n, self.corpus_batch):
+            idx = list(range(s, min(n, s + self.corpus_batch)))
+            batch = movie_dataset[idx]
+            x = batch.x.to(device)
+            tok = getattr(self.rq_vae, "tokenize", None)
+            blocks.append(tok(x) if tok is not None else self.rq_vae.get_semantic_ids(x).sem_ids)
+        sem_ids = torch.cat(blocks, dim=0) if blocks else torch.zeros((0, self.n_layers), dtype=torch.int64, device=device)
+        dedup = dedup_rank(sem_ids, self.codebook_size)
+        self.cached_ids = torch.cat([sem_ids, dedup.unsqueeze(1)], dim=1)
+        return self.cached_ids
+
+    def _tokenize_seq_batch_from_cached(self, ids: Tensor) -> Tensor:
+        n = ids.shape[1]
+        return self.cached_ids[ids.flatten(), :].reshape(ids.shape[0], n * self.cached_ids.shape[1])
+
+    @torch.no_grad
+    @eval_mode
+    def forward(self, batch: SeqBatch) -> TokenizedSeqBatch:
+        if self.cached_ids is None or batch.ids.max() >= self.cached_ids.shape[0]:
+            B, N = batch.ids.shape
+            sem_ids = self.rq_vae.get_semantic_ids(batch.x).sem_ids
+            D = sem_ids.shape[-1]
+            seq_mask, sem_ids_fut = None, None
+        else:
+            B, N = batch.ids.shape
+            _, D = self.cached_ids.shape
+            sem_ids = self._tokenize_seq_batch_from_cached(batch.ids)
+            seq_mask = batch.seq_mask.repeat_interleave(D, dim=1)
+            sem_ids[~seq_mask] = -1
+
+            sem_ids_fut = self._tokenize_seq_batch_from_cached(batch.ids_fut)
+
+        token_type_ids = torch.arange(D, device=sem_ids.device).repeat(B, N)
+        token_type_ids_fut = torch.arange(D, device=sem_ids.device).repeat(B, 1)
+        return TokenizedSeqBatch(
+            user_ids=batch.user_ids,
+            sem_ids=sem_ids,
+            sem_ids_fut=sem_ids_fut,
+            seq_mask=seq_mask,
+            token_type_ids=token_type_ids,
+            token_type_ids_fut=token_type_ids_fut,
+        )

@@ -1,0 +1,245 @@
+"""GPU tests of the module-level mirrors (Quantize / RqVae / MLP / Kmeans / SemanticIdTokenizer) against outputs of
+the unmodified reference modules (tests/golden/rqvae_c1.npz, tokenizer.npz) and the oracle.  `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+import inputs as I
+from oracle import rq_oracle as O
+from parity import assert_ids_match, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+T, BETA = 0.2, 0.25
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def build(mode_name, n_cat, Din=64, D=16, hidden=(32,), K=32, L=2, seed=320):
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode as M
+    mode = {"ste": M.STE, "rot": M.ROTATION_TRICK, "gumbel": M.GUMBEL_SOFTMAX}[mode_name]
+    m = RqVae(input_dim=Din, embed_dim=D, hidden_dims=list(hidden), codebook_size=K, codebook_kmeans_init=False,
+              codebook_mode=mode, n_layers=L, commitment_weight=BETA, n_cat_features=n_cat).cuda()
+    enc = I.mlp_weights(seed, [Din] + list(hidden) + [D])
+    dec = I.mlp_weights(seed + 1, [D] + list(hidden)[::-1] + [Din])
+    cbs = [(I.rand(seed + 10 + l, K, D) * (0.6 ** l) - (0.25 if l else 0.0)).astype(np.float32) for l in range(L)]
+    with torch.no_grad():
+        for lin, w in zip([mm for mm in m.encoder.mlp if isinstance(mm, torch.nn.Linear)], enc):
+            lin.weight.copy_(dev(w))
+        for lin, w in zip([mm for mm in m.decoder.mlp if isinstance(mm, torch.nn.Linear)], dec):
+            lin.weight.copy_(dev(w))
+        for layer, c in zip(m.layers, cbs):
+            layer.embedding.weight.copy_(dev(c))
+    return m, enc, dec, cbs
+
+
+def c1_inputs(n_cat):
+    g = load_golden("rqvae_c1")
+    B, Din, D, H, K, L = (int(v) for v in g["shape"])
+    x = I.randn(300, B, Din)
+    if n_cat:
+        x[:, -n_cat:] = (I.rand(301, B, n_cat) > 0.5).astype(np.float32)
+    us = [I.rand(310 + l, B, K) for l in range(L)]
+    return g, x, us
+
+
+def batch_of(x):
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    return SeqBatch(user_ids=None, ids=None, ids_fut=None, x=x, x_fut=None, seq_mask=None)
+
+
+@pytest.mark.parametrize("n_cat", [0, 4])
+def test_rqvae_eval_outputs_vs_reference(n_cat):
+    g, x, _ = c1_inputs(n_cat)
+    m, enc, dec, cbs = build("ste", n_cat)
+    m.eval()
+    with torch.no_grad():
+        so = m.get_semantic_ids(dev(x), T)
+        fo = m(batch_of(dev(x)), T)
+        tok = m.tokenize(dev(x))
+    res = O.mlp_forward(x, enc)
+    ids = host(so.sem_ids)
+    assert so.embeddings.shape == (x.shape[0], 16, 2) and so.residuals.shape == (x.shape[0], 16, 2)
+    assert so.sem_ids.dtype == torch.int64 and np.array_equal(ids, host(tok))
+    assert_ids_match(ids, g[f"cat{n_cat}_eval_sem_ids"], res, cbs)
+    same = (ids == g[f"cat{n_cat}_eval_sem_ids"]).all(1)
+    assert same.mean() > 0.995
+    assert rel_err(host(so.embeddings)[same], g[f"cat{n_cat}_eval_embeddings"][same]) < 1e-5
+    assert np.abs(host(so.residuals)[same] - g[f"cat{n_cat}_eval_residuals"][same]).max() < 1e-5
+    assert rel_err(host(so.quantize_loss)[same], g[f"cat{n_cat}_eval_qloss"][same]) < 1e-4
+    if same.all():
+        ref = g[f"cat{n_cat}_eval_losses"]
+        got = np.array([fo.loss.item(), fo.reconstruction_loss.item(), fo.rqvae_loss.item(), fo.p_unique_ids.item()])
+        assert np.allclose(got, ref, rtol=1e-5), (got, ref)
+        assert rel_err(host(fo.embs_norm), g[f"cat{n_cat}_eval_embs_norm"]) < 1e-5
+
+
+@pytest.mark.parametrize("n_cat", [0, 4])
+@pytest.mark.parametrize("mname", ["ste", "rot", "gumbel"])
+def test_rqvae_train_step_vs_reference(n_cat, mname, monkeypatch):
+    """forward() losses and the gradient of EVERY parameter against the reference's autograd."""
+    g, x, us = c1_inputs(n_cat)
+    m, *_ = build(mname, n_cat)
+    m.train()
+    if mname == "gumbel":
+        from rq_vae_recommender_b200.distributions import gumbel
+        queue = [dev(u) for u in us]
+        monkeypatch.setattr(gumbel, "draw_uniform", lambda shape, device: queue.pop(0))
+    fo = m(batch_of(dev(x)), T)
+    fo.loss.backward()
+    tag = f"cat{n_cat}_{mname}"
+    ref = g[f"{tag}_losses"]
+    got = np.array([fo.loss.item(), fo.reconstruction_loss.item(), fo.rqvae_loss.item(), fo.p_unique_ids.item()])
+    tol = 1e-4 if mname == "gumbel" else 2e-5
+    assert np.allclose(got, ref, rtol=tol), (got, ref)
+    assert rel_err(host(fo.embs_norm), g[f"{tag}_embs_norm"]) < (5e-4 if mname == "gumbel" else 1e-5)
+    gtol = 2e-3 if mname == "gumbel" else 1e-4
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        assert rel_err(host(p.grad), g[f"{tag}_grad_{name}"]) < gtol, name
+
+
+def test_state_dict_keys_and_checkpoint_roundtrip(tmp_path):
+    m, *_ = build("ste", 0, Din=768, D=32, hidden=(512, 256, 128), K=256, L=3)
+    keys = sorted(m.state_dict().keys())
+    assert keys == sorted([f"layers.{i}.embedding.weight" for i in range(3)] +
+                          [f"encoder.mlp.{i}.weight" for i in (0, 2, 4, 6)] +
+                          [f"decoder.mlp.{i}.weight" for i in (0, 2, 4, 6)])       # SURVEY 5.4 drop-in constraint
+    path = str(tmp_path / "ckpt.pt")
+    torch.save({"iter": 7, "model": m.state_dict(), "model_config": m.config}, path)
+    m2, *_ = build("ste", 0, Din=768, D=32, hidden=(512, 256, 128), K=256, L=3, seed=999)
+    m2.load_pretrained(path)
+    x = dev(I.unit_rows(5, 300, 768))
+    m.eval(); m2.eval()
+    assert torch.equal(m.tokenize(x), m2.tokenize(x))
+
+
+def test_quantize_module_api_and_kmeans_first_call():
+    from rq_vae_recommender_b200.modules.quantize import Quantize, QuantizeForwardMode, QuantizeOutput
+    from rq_vae_recommender_b200.init.kmeans import Kmeans
+    x = dev(I.randn(600, 4096, 16))
+    q = Quantize(embed_dim=16, n_embed=32, do_kmeans_init=True, forward_mode=QuantizeForwardMode.STE).cuda().train()
+    np.random.seed(610); torch.manual_seed(611)
+    out = q(x, temperature=T)
+    assert isinstance(out, QuantizeOutput) and q.kmeans_initted
+    np.random.seed(610); torch.manual_seed(611)
+    ref = Kmeans(k=32).run(x)
+    assert torch.allclose(q.embedding.weight, ref.centroids, atol=1e-6)
+    g = load_golden("kmeans")
+    assert np.abs(host(q.embedding.weight) - g["a_centroids"]).max() < 2e-5     # = the reference's k-means result
+    o = O.quantize_forward(host(x), host(q.embedding.weight), O.STE, True, T, BETA)
+    assert_ids_match(host(out.ids), o.ids, host(x), [host(q.embedding.weight)])
+    assert rel_err(host(out.loss), o.loss) < 1e-5
+    with pytest.raises(NotImplementedError):
+        from rq_vae_recommender_b200.modules.quantize import QuantizeDistance
+        Quantize(16, 32, do_kmeans_init=False, distance_mode=QuantizeDistance.COSINE).cuda()(x, T)
+
+
+def test_sim_vq_and_codebook_normalize_paths():
+    """out_proj = Linear (sim_vq) + L2 norm (codebook_normalize): gradients flow to embedding AND projection."""
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode
+    torch.manual_seed(0)
+    m = RqVae(input_dim=64, embed_dim=16, hidden_dims=[32], codebook_size=32, codebook_kmeans_init=False,
+              codebook_normalize=True, codebook_sim_vq=True, codebook_mode=QuantizeForwardMode.ROTATION_TRICK,
+              n_layers=2, n_cat_features=0).cuda().train()
+    assert "layers.0.out_proj.0.weight" in m.state_dict()
+    x = dev(I.randn(1, 256, 64))
+    fo = m(batch_of(x), T)
+    fo.loss.backward()
+    for name, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    # float64 torch re-statement of the same forward on the kernel's ids
+    so = m.get_semantic_ids(x, T)
+    cb0 = torch.nn.functional.normalize(m.layers[0].embedding.weight @ m.layers[0].out_proj[0].weight.T, dim=-1)
+    assert torch.allclose(m.layers[0].codebook(), cb0, atol=1e-6)
+
+
+def test_tokenizer_corpus_pass_vs_reference():
+    from rq_vae_recommender_b200.modules.tokenizer.semids import SemanticIdTokenizer, dedup_rank
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    g = load_golden("tokenizer")
+    N, Din, D, H, K, L = (int(v) for v in g["shape"])
+    x = I.randn(801, N, Din)
+    m, enc, dec, cbs = build("gumbel", 0, Din=Din, D=D, hidden=(H,), K=K, L=L, seed=800)
+    tok = SemanticIdTokenizer(input_dim=Din, output_dim=D, hidden_dims=[H], codebook_size=K, n_layers=L, n_cat_feats=0).cuda()
+    tok.rq_vae = m
+    tok.corpus_batch = 700          # ragged last batch
+
+    class Items:
+        def __len__(self):
+            return N
+        def __getitem__(self, idx):
+            idx = torch.as_tensor(idx)
+            return SeqBatch(user_ids=-torch.ones_like(idx), ids=idx.unsqueeze(0), ids_fut=-torch.ones_like(idx),
+                            x=torch.from_numpy(x)[idx], x_fut=-torch.ones_like(idx), seq_mask=torch.ones_like(idx, dtype=bool))
+    cached = host(tok.precompute_corpus_ids(Items()))
+    ref = g["cached_ids"].astype(np.int64)
+    assert cached.shape == ref.shape == (N, L + 1) and tok.sem_ids_dim == L + 1
+    res = O.mlp_forward(x, enc)
+    assert_ids_match(cached[:, :L], ref[:, :L], res, cbs)
+    if np.array_equal(cached[:, :L], ref[:, :L]):
+        assert np.array_equal(cached[:, L], ref[:, L])           # dedup column == the reference's O(N^2) result
+    assert np.array_equal(host(dedup_rank(dev(ref[:, :L]), K)), ref[:, L])
+    # sequence tokenisation from the cache (semids.py:112-146)
+    ids = torch.tensor([[3, 5, 7], [9, 11, 2]]).cuda()
+    b = SeqBatch(user_ids=torch.zeros(2).cuda(), ids=ids, ids_fut=torch.tensor([[1], [4]]).cuda(), x=None, x_fut=None,
+                 seq_mask=torch.tensor([[True, True, False], [True, True, True]]).cuda())
+    out = tok(b)
+    assert out.sem_ids.shape == (2, 3 * (L + 1)) and (out.sem_ids[0, -(L + 1):] == -1).all()
+    assert torch.equal(out.sem_ids[1, : L + 1], tok.cached_ids[9])
+    assert out.sem_ids_fut.shape == (2, L + 1) and out.token_type_ids.shape == (2, 3 * (L + 1))
+
+
+def test_training_loop_like_train_rqvae():
+    """The call sequence of train_rqvae.py:136-292 (k-means warm-up call, AdamW steps, eval, corpus ids + diversity
+    stats) on synthetic item features: the loss must fall and the id statistics must be well formed."""
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode
+    from rq_vae_recommender_b200.modules.tokenizer.semids import SemanticIdTokenizer
+    from rq_vae_recommender_b200 import parallel
+    np.random.seed(0); torch.manual_seed(0)
+    N, Din = 6000, 768
+    centers = I.unit_rows(40, 64, Din)
+    items = centers[np.random.RandomState(1).randint(0, 64, N)] + 0.3 * I.unit_rows(41, N, Din)
+    items = dev((items / np.linalg.norm(items, axis=1, keepdims=True)).astype(np.float32))
+    model = RqVae(input_dim=Din, embed_dim=32, hidden_dims=[512, 256, 128], codebook_size=256,
+                  codebook_kmeans_init=True, codebook_mode=QuantizeForwardMode.STE, n_layers=3, n_cat_features=0).cuda()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    model.train()
+    model(batch_of(items[:4000]), 0.2)                      # train_rqvae.py:178-183: lazy k-means init of all levels
+    assert all(l.kmeans_initted for l in model.layers)
+    losses = []
+    for it in range(40):
+        idx = torch.randint(0, N, (640,), device="cuda")
+        opt.zero_grad()
+        out = model(batch_of(items[idx]), gumbel_t=0.2)
+        out.loss.backward()
+        opt.step()
+        losses.append(out.loss.item())
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+    model.eval()
+    with torch.no_grad():
+        ev = model(batch_of(items[:640]), gumbel_t=0.2)
+    assert 0 < ev.p_unique_ids.item() <= 1 and ev.embs_norm.shape == (640, 3)
+    tok = SemanticIdTokenizer(input_dim=Din, output_dim=32, hidden_dims=[512, 256, 128], codebook_size=256, n_layers=3,
+                              n_cat_feats=0).cuda()
+    tok.rq_vae = model
+
+    class Items:
+        def __len__(self):
+            return N
+        def __getitem__(self, idx):
+            return batch_of(items[torch.as_tensor(idx).cuda()])
+    corpus = tok.precompute_corpus_ids(Items())
+    assert corpus.shape == (N, 4)
+    usage = parallel.codebook_usage(corpus[:, :3].contiguous(), 256)
+    assert usage.shape == (3, 256) and usage.sum(1).tolist() == [N] * 3
+    _, counts = torch.unique(corpus[:, :-1], dim=0, return_counts=True)        # train_rqvae.py:279-283
+    assert counts.max().item() - 1 == corpus[:, -1].max().item()
