@@ -157,8 +157,11 @@ def test_sim_vq_and_codebook_normalize_paths():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
     # float64 torch re-statement of the same forward on the kernel's ids
     so = m.get_semantic_ids(x, T)
-    cb0 = torch.nn.functional.normalize(m.layers[0].embedding.weight @ m.layers[0].out_proj[0].weight.T, dim=-1)
-    assert torch.allclose(m.layers[0].codebook(), cb0, atol=1e-6)
+    # (float64: rqvae.py sets float32 matmul precision "high" like the reference, so a float32 `@` here would be TF32)
+    w64 = m.layers[0].embedding.weight.double() @ m.layers[0].out_proj[0].weight.double().T
+    cb0 = torch.nn.functional.normalize(w64, dim=-1)
+    assert torch.allclose(m.layers[0].codebook().double(), cb0, atol=1e-6)
+    assert so.sem_ids.shape == (256, 2)
 
 
 def test_tokenizer_corpus_pass_vs_reference():
