@@ -10,7 +10,7 @@ own shard (items are independent: weak scaling, no data-path collective); the ti
   value     items/s with the batch already resident in HBM (CUDA events around the K steps)
   e2e       items/s through the public host API (pinned host rows -> H2D -> kernels -> D2H ids inside the timing)
   roofline  algorithmic HBM bytes of the dominant kernel / its event-timed duration vs MEASURED_PEAKS.json
-  cpu_baseline  the numpy oracle port of the reference path timed on this host's cores (bounded sample)
+  cpu_baseline  the torch-CPU port of the reference path (oracle/rq_oracle_torch.py) on this host's cores, bounded sample
 
 --impl reference times that CPU port as the reference arm (the reference is pure Python/PyTorch: there is nothing
 to compile into oracle/_ref).
@@ -93,36 +93,48 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_items_per_sec(x, cbs, budget_s=12.0, sample=16384):
-    """The reference's CPU path (oracle port: same op sequence as quantize.py:113-128 + rqvae.py:125-130) on a
-    bounded sample of the same workload."""
-    from oracle import rq_oracle as O
-    xs = x[:sample]
-    O.rq_tokenize(xs[:2048], cbs)
+def cpu_threads():
+    import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_port_items_per_sec(x, cbs, budget_s=12.0, sample=65536):
+    """The reference's CPU path (torch-CPU port, op for op quantize.py:113-128 + rqvae.py:125-132, eager fp32, all host
+    threads) on a bounded sample of the same workload."""
+    import torch
+    from oracle import rq_oracle_torch as OT
+    threads = cpu_threads()
+    xs = torch.from_numpy(x[:sample])
+    cbt = [torch.from_numpy(c) for c in cbs]
+    OT.rq_tokenize(xs, cbt)                   # full-size warm-up: steady state, not first-touch page faults
     t0 = time.perf_counter()
     n = 0
     while True:
-        O.rq_tokenize(xs, cbs)
+        OT.rq_tokenize(xs, cbt)
         n += len(xs)
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= 16 * sample:
             break
-    return n / dt, f"{n} items ({n // len(xs)} passes over {len(xs)} rows of the same synthetic batch), {dt:.1f}s"
+    return n / dt, threads, f"{n} items ({n // len(xs)} passes over {len(xs)} rows of the same synthetic batch), {dt:.1f}s"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    x, cbs = make_problem(16384)
-    from oracle import rq_oracle as O
-    cores = os.cpu_count()
-    sample = 16384
-    for _ in range(args.warmup):
-        O.rq_tokenize(x[:4096], cbs)
+    import torch
+    from oracle import rq_oracle_torch as OT
+    sample = 65536
+    x, cbs = make_problem(sample)
+    cores = cpu_threads()
+    xt, cbt = torch.from_numpy(x), [torch.from_numpy(c) for c in cbs]
+    for _ in range(max(args.warmup, 1)):      # full-size warm-up: steady state, not first-touch page faults
+        OT.rq_tokenize(xt, cbt)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.rq_tokenize(x[:sample], cbs)
+        OT.rq_tokenize(xt, cbt)
     dt = time.perf_counter() - t0
     val = args.steps * sample / dt
     print(json.dumps({
@@ -131,7 +143,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{sample} rows per step"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} rows of the same synthetic batch (numpy/BLAS threads)"},
+                         "sample": f"{args.steps} steps x {sample} rows of the same synthetic batch (torch CPU eager fp32)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -237,8 +249,8 @@ def main():
                          "kernel_ms": kern_ms, "algorithmic_bytes": algorithmic_bytes(N_ITEMS)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, sample = cpu_port_items_per_sec(x_h, cbs_h)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+            v, threads, sample = cpu_port_items_per_sec(x_h, cbs_h)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         # sanity: the timed result is the real answer
         from oracle import rq_oracle as O
         chk = O.rq_tokenize(x_h[:512], cbs_h)

@@ -93,7 +93,20 @@ class CorpusTokenizer:
         return all_gather_rows(ids_local.to(torch.int32), n_total, group).to(torch.int64)
 
     def measured_traffic_bytes(self):
-        return None
+        """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the 65 536 x 768 bench shape,
+        from the committed `ncu --set full` capture (profiles/); None when no capture covers the active kernel."""
+        import csv
+        import os
+        if not self.use_tc:
+            return None
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                            "r1_prof_tc_r1e_summary.csv")
+        try:
+            vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return int(sum(v * scale[u] for u, v in vals.values()))
+        except Exception:
+            return None
 
 
 def all_gather_rows(block: torch.Tensor, n_total: int, group=None) -> torch.Tensor:

@@ -173,3 +173,15 @@ def test_tokenizer_dedup_column():
     assert ref[:, L].max() > 3          # the fixture really exercises duplicates
     usage = O.codebook_usage(ref[:, :L], K)
     assert usage.sum(1).tolist() == [N] * L
+
+
+def test_torch_cpu_port_matches_numpy_oracle_and_reference():
+    """The torch-CPU port used for the CPU baseline timing gives the reference's ids."""
+    import torch
+    from oracle import rq_oracle_torch as OT
+    g = load_golden("rq_ns2048")
+    n, D, K, L = (int(v) for v in g["shape"])
+    x, cbs = I.rq_problem(n, D, K, L, seed=1234)
+    ids = OT.rq_tokenize(torch.from_numpy(x), [torch.from_numpy(c) for c in cbs]).numpy()
+    assert_ids_match(ids, g["eval_ids"], x, cbs)
+    assert_ids_match(ids, O.rq_tokenize(x, cbs), x, cbs)
