@@ -41,6 +41,7 @@ class CorpusTokenizer:
         self.encoder = encoder
         self.chunk_rows = chunk_rows
         self._copy_stream = None
+        self._host_out = None
 
     # ---- device resident rows
     @torch.no_grad()
@@ -57,8 +58,10 @@ class CorpusTokenizer:
         """Double-buffered: chunk i+1 is copied host->device on a side stream while chunk i is quantised."""
         n = x_host.shape[0]
         dev = self.codebooks[0].device
-        if out is None:
-            out = torch.empty((n, self.L), dtype=torch.int64).pin_memory()
+        if out is None:                       # pinned result buffer, allocated once per size (cudaHostAlloc is slow)
+            if self._host_out is None or self._host_out.shape[0] != n:
+                self._host_out = torch.empty((n, self.L), dtype=torch.int64).pin_memory()
+            out = self._host_out
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
