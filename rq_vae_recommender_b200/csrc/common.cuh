@@ -94,15 +94,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// same, but a wait longer than ~2 s (a protocol bug, never legitimate) traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity, int tag) {
+// same, but a wait longer than ~2 s (a protocol bug, never legitimate) traps instead of hanging the GPU.
+// No printf here: it would force a stack frame and spills into the single-thread MMA / producer loops.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity, int /*tag*/) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("rqb200: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map): SASS UBLKCP

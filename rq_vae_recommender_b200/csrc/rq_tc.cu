@@ -34,9 +34,9 @@ extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float a
 #define TC_BSTAGES 2
 #define TC_BSTAGE_BYTES (128 * TC_KC * 2)   // 128 codes x 64 k x fp16 = 16 KB
 #define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
-#define TC_NCONV_WARPS 8
+#define TC_NCONV_WARPS 4
 #define TC_NEPI_WARPS 8
-#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 8 converters | 8 epilogue (2 per TMEM lane quarter)
+#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 4 converters | 8 epilogue (2 per TMEM lane quarter) = 512 threads
 #define TC_Z 6.0f         // margin multiplier on the statistical fp16 rounding bound
 
 struct TcLevelConst {
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       mbar_init(&ms->t_full[i][1], 1);
       mbar_init(&ms->t_empty[i], TC_NEPI_WARPS * 32);
     }
-    mbar_init(&ms->rowinfo_free, TC_NEPI_WARPS * 32);
+    mbar_init(&ms->rowinfo_free, 128);   // the half-0 epilogue thread of every row
     fence_mbar_init();
   }
   if (warp == 1) tc_alloc(&ms->tmem_base, 512);
@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
   if (warp < 4) {
     // ============================================================== warpgroup 0: B producer (warp 0), MMA issuer (warp 1)
-    // register budget (per-CTA pool = 640 threads x 96 at launch = 61440): 128x32 + 256x96 + 256x128 = 61440
+    // register budget (per-CTA pool = 512 threads x 128 at launch = 65536): 128x32 + 128x128 + 256x176 = 65536.
+    // With the 225 KB shared-memory carve-out there is no L1: a spill is an L2 round trip, so no role may spill in a loop.
     tc_setmaxnreg_dec<32>();
     if (warp == 0 && lane == 0) {
       uint32_t s = 0;
@@ -392,46 +393,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       }
     }
   } else if (warp < 4 + TC_NCONV_WARPS) {
-    // ============================================================== warpgroups 1-2: x fp32 -> fp16 swizzled A chunks
-    const int cw = warp - 4;                 // rows 16*cw .. 16*cw+15
-    const int sub = lane >> 4, q = lane & 15;  // lane -> (row parity, float4 index inside the 64-float chunk row)
+    // ============================================================== warpgroup 1: x fp32 -> fp16 swizzled A chunks
+    // Warp cw owns rows [32cw, 32cw+32) of every chunk.  Lane -> row 4i + (lane >> 3), i = 0..7 (8 rows per lane, so the
+    // row statistics are 16 registers) and float4 column (lane & 7) + 8j: half-unit j = 0/1 is 8 x LDG.128 per lane,
+    // each warp instruction reading four 128-byte segments.  The two register buffers leapfrog, so 8..16 loads per
+    // lane are always in flight and nothing is copied.
+    // (stays at the launch allocation of 128 registers: at 96 this loop spilled its row pointers -> L2 latency per chunk)
+    const int cw = warp - 4;
+    const int rsub = lane >> 3, q8 = lane & 7;
     const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
     uint32_t it = 0;
-    long long c_wait = 0, c_work = 0;
+    long long c_wait = 0, c_work = 0, c_ldwait = 0, c_cvt = 0;
     TC_T0(tcv);
     const long long tcv_start = tcv;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int row_base = tile * TC_BM + cw * 16;
+      const int row_base = tile * TC_BM + cw * 32 + rsub;
       float s4[8], s2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s4[i] = 0.f; s2[i] = 0.f; }
-      float4 v[8];
-      auto load_chunk = [&](int kc) {
+      float4 va[8], vb[8];
+      // half-unit h: chunk kc = h >> 1, float4 columns 8*(h & 1) + q8, rows row_base + 4i
+      auto load_half = [&](float4 (&v)[8], int h) {
+        const int kc = h >> 1, f = q8 + 8 * (h & 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = row_base + 2 * i + sub;
+          const int row = row_base + 4 * i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row < p.B) {
-            const float* src = p.x + (int64_t)row * p.ldx + kc * TC_KC + q * 4;
+            const float* src = p.x + (int64_t)row * p.ldx + kc * TC_KC + f * 4;
             if (vec_ok) v[i] = ldg_stream(reinterpret_cast<const float4*>(src));
             else { v[i].x = __ldg(src); v[i].y = __ldg(src + 1); v[i].z = __ldg(src + 2); v[i].w = __ldg(src + 3); }
           }
         }
       };
-      load_chunk(0);
-      for (int kc = 0; kc < nkc; ++kc) {
-        float4 cur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = v[i];
-        if (kc + 1 < nkc) load_chunk(kc + 1);          // prefetch the next chunk while this one is converted
-        TC_ACC(c_work, tcv);
-        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
-        TC_ACC(c_wait, tcv);
-        unsigned char* dst = sA + kc * TC_ACHUNK_BYTES;
+      auto convert_half = [&](const float4 (&v)[8], int h) {
+        unsigned char* dst = sA + (h >> 1) * TC_ACHUNK_BYTES;
+        const uint32_t f = q8 + 8 * (h & 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = cw * 16 + 2 * i + sub;
-          const float4 a = cur[i];
+          const int r = cw * 32 + rsub + 4 * i;
+          const float4 a = v[i];
           const float a2x = a.x * a.x, a2y = a.y * a.y, a2z = a.z * a.z, a2w = a.w * a.w;
           s2[i] += (a2x + a2y) + (a2z + a2w);
           s4[i] += (a2x * a2x + a2y * a2y) + (a2z * a2z + a2w * a2w);
@@ -442,20 +443,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           if (((b0 & 0x7c00u) == 0x7c00u) || ((b0 & 0x7c000000u) == 0x7c000000u) || ((b1 & 0x7c00u) == 0x7c00u) ||
               ((b1 & 0x7c000000u) == 0x7c000000u))
             s4[i] = INFINITY;
-          const uint32_t off = r * 128 + ((((uint32_t)q >> 1) ^ (r & 7)) << 4) + (q & 1) * 8;
+          const uint32_t off = r * 128 + (((f >> 1) ^ (r & 7)) << 4) + (f & 1) * 8;
           *reinterpret_cast<uint2*>(dst + off) = make_uint2(b0, b1);
         }
+      };
+      const int nh = 2 * nkc;
+      load_half(va, 0);
+      load_half(vb, 1);
+#pragma unroll 1
+      for (int kc = 0; kc < nkc; ++kc) {
+        TC_ACC(c_work, tcv);
+        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
+        TC_ACC(c_wait, tcv);
+        if (trace) {   // split "waiting for the loads to land" from "convert + store": shfl needs the last-issued value
+          const float probe = __shfl_sync(0xffffffffu, va[7].w, 0);
+          asm volatile("" ::"f"(probe));
+          TC_ACC(c_ldwait, tcv);
+        }
+        convert_half(va, 2 * kc);
+        TC_ACC(c_cvt, tcv);
+        if (2 * kc + 2 < nh) load_half(va, 2 * kc + 2);
+        if (trace) {
+          const float probe = __shfl_sync(0xffffffffu, vb[7].w, 0);
+          asm volatile("" ::"f"(probe));
+          TC_ACC(c_ldwait, tcv);
+        }
+        convert_half(vb, 2 * kc + 1);
+        TC_ACC(c_cvt, tcv);
+        if (2 * kc + 3 < nh) load_half(vb, 2 * kc + 3);
         if (kc == nkc - 1) {
           // row statistics for the margin: reduce over the 16 lanes that share a row, publish before the last arrive
           mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = 4; o > 0; o >>= 1) {      // the 8 lanes (q8) that share row 4i + rsub
               s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], o);
               s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
             }
-            if (q == 0) ms->rowinfo[cw * 16 + 2 * i + sub] = (tc_bf16_up(s4[i]) << 16) | tc_bf16_up(s2[i]);
+            if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * i] = (tc_bf16_up(s4[i]) << 16) | tc_bf16_up(s2[i]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -464,11 +490,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     }
     if (trace && cw == 0 && lane == 0) {
       tc_trace_add(p.stats, 9, c_wait); tc_trace_add(p.stats, 10, clock64() - tcv_start);
+      tc_trace_add(p.stats, 20, c_ldwait); tc_trace_add(p.stats, 21, c_cvt);
     }
   } else {
     // ============================================================== warpgroups 3-4: scores -> candidates -> exact re-rank -> ids
     // two warps per TMEM lane quarter: `half` 0 scans columns [0,128) and owns merge / re-rank / ids, half 1 scans [128,256)
-    tc_setmaxnreg_inc<128>();
+    tc_setmaxnreg_inc<176>();
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
     const int half = (warp - (4 + TC_NCONV_WARPS)) >> 2;
     const int r_local = quarter * 32 + lane;
@@ -476,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const int bar_x = 2 + quarter;      // half 1 -> half 0: exch[] written
     const int bar_i = 6 + quarter;      // half 0 -> half 1: the level's id is final (written into exch[].idx)
     uint32_t g = 0, it = 0;
-    long long e_tf = 0, e_scan = 0, e_pair = 0, e_rr = 0, e_idw = 0;
+    long long e_tf = 0, e_scan = 0, e_pair = 0, e_rr = 0, e_idw = 0, e_merge = 0, e_many = 0;
     TC_T0(te);
     const long long te_start = te;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -496,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         mbar_wait_guarded(&ms->t_full[buf][half], u & 1, 7);
         TC_ACC(e_tf, te);
         tc_fence_after();
-        if (l == 0) {
+        if (l == 0 && half == 0) {       // only the merging warp needs the margin
           const uint32_t ri = ms->rowinfo[r_local];
           x4s = __uint_as_float(ri & 0xffff0000u);
           x2s = __uint_as_float(ri << 16);
@@ -514,34 +541,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
         float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
         int i1 = 0, i2 = 0;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t sr[32];
-          tc_ld32_issue(tcol + c * 32, sr);
-          float4 ta[8], tb[8];
+        // T rows for one 32-column chunk: all loads of the chunk issued back to back (<= 16 x LDG.128 in flight)
+        auto load_t = [&](float4 (&ta)[8], int c) {
           if (valid) {
 #pragma unroll
             for (int v4 = 0; v4 < 8; ++v4) ta[v4] = __ldg(reinterpret_cast<const float4*>(trow0 + c * 32) + v4);
-          } else {
+            if (l >= 2) {
+              float4 tb[8];
 #pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (valid && l >= 2) {
+              for (int v4 = 0; v4 < 8; ++v4) tb[v4] = __ldg(reinterpret_cast<const float4*>(trow1 + c * 32) + v4);
 #pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) tb[v4] = __ldg(reinterpret_cast<const float4*>(trow1 + c * 32) + v4);
-#pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) { ta[v4].x += tb[v4].x; ta[v4].y += tb[v4].y; ta[v4].z += tb[v4].z; ta[v4].w += tb[v4].w; }
-          }
-          for (int j = 2; j < l; ++j) {   // L > 3 only
-            const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + half * 128 + c * 32;
-            if (valid) {
+              for (int v4 = 0; v4 < 8; ++v4) { ta[v4].x += tb[v4].x; ta[v4].y += tb[v4].y; ta[v4].z += tb[v4].z; ta[v4].w += tb[v4].w; }
+            }
+            for (int j = 2; j < l; ++j) {   // L > 3 only
+              const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + half * 128 + c * 32;
 #pragma unroll
               for (int v4 = 0; v4 < 8; ++v4) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(gj) + v4);
                 ta[v4].x += t.x; ta[v4].y += t.y; ta[v4].z += t.z; ta[v4].w += t.w;
               }
             }
+          } else {
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        };
+        auto score_chunk = [&](const float4 (&ta)[8], int c) {
+          uint32_t sr[32];
+          tc_ld32_issue(tcol + c * 32, sr);
           tc_ld_wait();
           if (valid) {
             // chunk-local top-3 with immediate indices, then one merge into the running top-3
@@ -559,6 +586,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
             tc_insert(q2, kb + j2, m1, m2, m3, i1, i2);
             m3 = fminf(m3, fmaxf(m2, q3)); // q3 >= q2: it can only displace m3
           }
+        };
+        {
+          // software pipeline over the 4 chunks: the next chunk's Gram rows are in flight while this one is scored
+          float4 t0[8], t1[8];
+          load_t(t0, 0);
+          load_t(t1, 1);
+          score_chunk(t0, 0);
+          load_t(t0, 2);
+          score_chunk(t1, 1);
+          load_t(t1, 3);
+          score_chunk(t0, 2);
+          score_chunk(t1, 3);
         }
 
         TC_ACC(e_scan, te);
@@ -591,6 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         uint32_t mask[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) mask[c] = 0;
+        TC_ACC(e_merge, te);
         if (mn) {
           // second pass over all 256 scores (warp-uniform branch): exact candidate bitmask for the `many` rows
           const uint32_t tall = tmem + lane_addr + buf * 256;
@@ -616,6 +656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
             mask[c] = mw;
           }
         }
+        TC_ACC(e_many, te);
         tc_fence_before();
         mbar_arrive(&ms->t_empty[buf]);     // accumulator buffer may be overwritten by level l+2
 
@@ -708,6 +749,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
       const int o = half ? 13 : 4;     // half 0 -> slots 4..8, half 1 -> slots 13..17
       tc_trace_add(p.stats, o + 0, e_tf); tc_trace_add(p.stats, o + 1, e_scan); tc_trace_add(p.stats, o + 2, half ? e_idw : e_pair);
       tc_trace_add(p.stats, o + 3, e_rr); tc_trace_add(p.stats, o + 4, clock64() - te_start);
+      if (!half) { tc_trace_add(p.stats, 18, e_merge); tc_trace_add(p.stats, 19, e_many); }
     }
   }
 
