@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 
 extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda,
                             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int relu,
@@ -259,7 +260,7 @@ struct TcParams {
   const unsigned char* blob;
   int64_t* ids;         // [B][L]
   int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
-  float sx;             // power-of-two scale applied to x before fp16 conversion
+  float sx;             // scale of the fp16 image of x; fixed at 1 (kept in the margin formulas for a future per-call scale)
 };
 
 struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
@@ -272,7 +273,7 @@ struct TcSmemMisc {
   uint64_t rowinfo_free;
   uint32_t tmem_base;
   uint32_t pad;
-  uint32_t rowinfo[TC_BM];        // bf16x2 (rounded up): sum x^4 | sum x^2 of the tile being scored
+  uint32_t rowinfo[TC_BM];        // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
   TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
 };
 
@@ -307,6 +308,8 @@ __device__ __forceinline__ void tc_insert(float a, int k, float& m1, float& m2, 
   i1 = lt1 ? k : i1;
 }
 
+// kTrace = true compiles the clock64 role accounting in (RQB200_TC_TRACE=1); the production instantiation carries none of it
+template <bool kTrace>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
-  const bool trace = p.stats != nullptr && p.stats[3] != 0;
+  const bool trace = kTrace && p.stats != nullptr;
 
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ms->tmem_base;
+  #define TC_TMEM_BASE() (*reinterpret_cast<volatile uint32_t*>(&ms->tmem_base))
 
   if (warp < 4) {
     // ============================================================== warpgroup 0: B producer (warp 0), MMA issuer (warp 1)
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           TC_ACC(w_te, tm);
           tc_fence_after();
           for (int h = 0; h < 2; ++h) {
-            const uint32_t d_tmem = tmem + buf * 256 + h * 128;
+            const uint32_t d_tmem = TC_TMEM_BASE() + buf * 256 + h * 128;
             for (int kc = 0; kc < nkc; ++kc, ++s) {
               TC_ACC(w_issue, tm);
               if (l == 0 && h == 0) mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
@@ -408,43 +411,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const long long tcv_start = tcv;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row_base = tile * TC_BM + cw * 32 + rsub;
-      float s4[8], s2[8];
+      // row statistics for the filter margin: max|x| and sum x^2 (sum x^4 <= max|x|^2 * sum x^2 is used downstream; max|x|
+      // doubles as the fp16 overflow test, NaN inputs surface through sum x^2).  ~half the ALU of tracking sum x^4 and
+      // testing every converted half for inf.
+      float sm[8], s2[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s4[i] = 0.f; s2[i] = 0.f; }
+      for (int i = 0; i < 8; ++i) { sm[i] = 0.f; s2[i] = 0.f; }
       float4 va[8], vb[8];
-      // half-unit h: chunk kc = h >> 1, float4 columns 8*(h & 1) + q8, rows row_base + 4i
+      // half-unit h: chunk kc = h >> 1, float4 columns 8*(h & 1) + q8, rows row_base + 4i.
+      // Register-frugal on purpose (a spill here is an L2 round trip per chunk): ONE 64-bit base pointer, the row
+      // stride, and compile-time multiples of it; shared-memory offsets are one base plus immediates -- the swizzle term
+      // (chunk ^ (row & 7)) only depends on the parity of i because rows advance by 4.
+      const float* xrow = p.x + (int64_t)row_base * p.ldx + q8 * 4;     // row_base + 0, float4 column q8
+      const int nvalid = p.B - row_base;                                 // row 4i is valid iff 4i < nvalid
+      const int64_t stride4 = 4 * p.ldx;
       auto load_half = [&](float4 (&v)[8], int h) {
-        const int kc = h >> 1, f = q8 + 8 * (h & 1);
+        const float* src0 = xrow + (h >> 1) * TC_KC + (h & 1) * 32;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = row_base + 4 * i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < p.B) {
-            const float* src = p.x + (int64_t)row * p.ldx + kc * TC_KC + f * 4;
+          if (4 * i < nvalid) {
+            const float* src = src0 + i * stride4;
             if (vec_ok) v[i] = ldg_stream(reinterpret_cast<const float4*>(src));
             else { v[i].x = __ldg(src); v[i].y = __ldg(src + 1); v[i].z = __ldg(src + 2); v[i].w = __ldg(src + 3); }
           }
         }
       };
+      const uint32_t srow = (uint32_t)(cw * 32 + rsub) * 128;            // byte offset of row (cw*32 + rsub) in a chunk
       auto convert_half = [&](const float4 (&v)[8], int h) {
-        unsigned char* dst = sA + (h >> 1) * TC_ACHUNK_BYTES;
         const uint32_t f = q8 + 8 * (h & 1);
+        // 16-byte chunk position after the 128B swizzle, for even / odd i (row & 7 = rsub or rsub + 4)
+        const uint32_t base_e = smem_u32(sA) + (h >> 1) * TC_ACHUNK_BYTES + srow + (((f >> 1) ^ (uint32_t)rsub) << 4) + (f & 1) * 8;
+        const uint32_t base_o = base_e ^ (4u << 4);                      // (c ^ (rsub + 4)) = (c ^ rsub) ^ 4 since rsub < 4
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int r = cw * 32 + rsub + 4 * i;
           const float4 a = v[i];
-          const float a2x = a.x * a.x, a2y = a.y * a.y, a2z = a.z * a.z, a2w = a.w * a.w;
-          s2[i] += (a2x + a2y) + (a2z + a2w);
-          s4[i] += (a2x * a2x + a2y * a2y) + (a2z * a2z + a2w * a2w);
-          const __half2 h0 = __floats2half2_rn(a.x * p.sx, a.y * p.sx);
-          const __half2 h1 = __floats2half2_rn(a.z * p.sx, a.w * p.sx);
-          // fp16 overflow / non-finite input: poison the row statistics -> every code becomes a candidate
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&h0), b1 = *reinterpret_cast<const uint32_t*>(&h1);
-          if (((b0 & 0x7c00u) == 0x7c00u) || ((b0 & 0x7c000000u) == 0x7c000000u) || ((b1 & 0x7c00u) == 0x7c00u) ||
-              ((b1 & 0x7c000000u) == 0x7c000000u))
-            s4[i] = INFINITY;
-          const uint32_t off = r * 128 + (((f >> 1) ^ (r & 7)) << 4) + (f & 1) * 8;
-          *reinterpret_cast<uint2*>(dst + off) = make_uint2(b0, b1);
+          s2[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, s2[i]))));
+          sm[i] = fmaxf(fmaxf(sm[i], fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+          const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+          const uint32_t addr = ((i & 1) ? base_o : base_e) + i * 512;   // rows advance by 4 -> 4 * 128 bytes
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h0)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h1)) : "memory");
         }
       };
       const int nh = 2 * nkc;
@@ -478,10 +485,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           for (int i = 0; i < 8; ++i) {
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {      // the 8 lanes (q8) that share row 4i + rsub
-              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], o);
+              sm[i] = fmaxf(sm[i], __shfl_xor_sync(0xffffffffu, sm[i], o));
               s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
             }
-            if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * i] = (tc_bf16_up(s4[i]) << 16) | tc_bf16_up(s2[i]);
+            if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * i] = (tc_bf16_up(sm[i]) << 16) | tc_bf16_up(s2[i]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -525,8 +532,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         tc_fence_after();
         if (l == 0 && half == 0) {       // only the merging warp needs the margin
           const uint32_t ri = ms->rowinfo[r_local];
-          x4s = __uint_as_float(ri & 0xffff0000u);
-          x2s = __uint_as_float(ri << 16);
+          const float xmax = __uint_as_float(ri & 0xffff0000u);        // max|x| (bf16, rounded up)
+          x2s = __uint_as_float(ri << 16);                              // sum x^2 (bf16, rounded up; NaN if any input is)
+          x4s = (xmax * p.sx < 65504.f) ? xmax * xmax * x2s : INFINITY;  // sum x^4 <= max|x|^2 sum x^2; fp16 overflow/inf -> poison
           mbar_arrive(&ms->rowinfo_free);
         }
         // ---- margin (DESIGN.md "filter error bound"): eps bounds |approx dot - exact dot|; scores are half-distances
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float eps = TC_Z * sig + flo + acc + lc.gerr;
         const float margin = 2.f * eps;
         const float ninv = -1.f / (p.sx * lc.sc);
-        const uint32_t tcol = tmem + lane_addr + buf * 256 + half * 128;
+        const uint32_t tcol = TC_TMEM_BASE() + lane_addr + buf * 256 + half * 128;
 
         float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
         int i1 = 0, i2 = 0;
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         TC_ACC(e_merge, te);
         if (mn) {
           // second pass over all 256 scores (warp-uniform branch): exact candidate bitmask for the `many` rows
-          const uint32_t tall = tmem + lane_addr + buf * 256;
+          const uint32_t tall = TC_TMEM_BASE() + lane_addr + buf * 256;
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {
             uint32_t sr[32];
@@ -757,7 +765,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem, 512);
+    tc_dealloc(TC_TMEM_BASE(), 512);
   }
 }
 
@@ -789,9 +797,15 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
     RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const size_t smem = (size_t)TC_MAX_KC * TC_ACHUNK_BYTES + TC_BSTAGES * TC_BSTAGE_BYTES + sizeof(TcSmemMisc);
-  RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
   const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-  rq_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  if (want_trace && stats) {       // caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
+    RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rq_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  } else {
+    RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rq_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+  }
   RQB_LAUNCH_CHECK();
   return RQB_OK;
 }
