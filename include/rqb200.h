@@ -114,6 +114,18 @@ int rqb200_l2norm_fwd(const float* x, float* y, float* norms, int B, int D, floa
 int rqb200_l2norm_bwd(const float* gy, const float* y, const float* norms, float* gx, int B, int D, float eps,
                       void* stream);
 
+/* ---- bf16 tensor-core GEMM for the MLPs (modules/encoder.py:23-38), reduced-precision / AMP-like, forward only ---
+ * The reference runs these Linears in bf16 when mixed precision is on (train_rqvae.py:36,69).  Operands live in HBM
+ * as "images": [tile of 128 rows][64-wide k chunk][128 x 128 B], the exact K-major SWIZZLE_128B shared-memory layout
+ * tcgen05 reads, so a pipeline stage is one contiguous TMA bulk copy.  K must be a multiple of 64.
+ *   f32_to_bf16_image : fp32 row-major [rows,K] -> image (used for the input x AND for a weight W[N,K]);
+ *   gemm_bf16         : Y = act(X W^T), fp32 accumulate; Y is written as the next layer's A image (N % 64 == 0)
+ *                       and/or as fp32 row-major [M,N]. */
+size_t rqb200_bf16_image_bytes(int rows, int K);
+int rqb200_f32_to_bf16_image(const float* x, int64_t ldx, int rows, int K, void* image, void* stream);
+int rqb200_gemm_bf16(const void* a_image, const void* w_image, int M, int N, int K, int relu, void* out_image,
+                     float* out_f32, int64_t ldo, void* stream);
+
 /* ---- corpus id statistics (train_rqvae.py:279-289, modules/tokenizer/semids.py:94-108) ---------------- */
 int rqb200_sid_histogram(const int64_t* ids, int B, int L, int K, int64_t* hist /* [L,K], zeroed here */,
                          void* stream);

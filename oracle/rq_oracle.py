@@ -341,3 +341,26 @@ def codebook_usage(sem_ids: np.ndarray, K: int) -> np.ndarray:
     """train_rqvae.py:285-289: per-level histogram of used codes -> [L,K] int64."""
     L = sem_ids.shape[1]
     return np.stack([np.bincount(sem_ids[:, l], minlength=K) for l in range(L)]).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- reduced-precision (AMP-like) MLP
+def round_bf16(a: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to bfloat16, returned as float32 (what cvt.rn.bf16.f32 does)."""
+    b = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((b + 0x7FFF + ((b >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
+def mlp_forward_bf16(x: np.ndarray, weights: Sequence[np.ndarray], normalize: bool = False) -> np.ndarray:
+    """modules/encoder.py:23-38 as the reference computes it under bf16 autocast (train_rqvae.py:36,69): operands rounded
+    to bf16, products accumulated in higher precision, ReLU, activations re-rounded to bf16 between layers; the last
+    layer's output stays fp32."""
+    h = round_bf16(x)
+    n = len(weights)
+    for i, w in enumerate(weights):
+        y = (h.astype(np.float64) @ round_bf16(w).astype(np.float64).T).astype(np.float32)
+        if i != n - 1:
+            h = round_bf16(np.maximum(y, 0))
+        else:
+            h = y
+    return l2norm(h) if normalize else h

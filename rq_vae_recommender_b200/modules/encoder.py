@@ -5,6 +5,7 @@ shipped checkpoints; forward() bypasses it and runs the whole stack as one autog
 with the ReLU fused in its epilogue (ops.MLPFunction)."""
 from typing import List
 
+import torch
 from torch import nn
 from torch import Tensor
 
@@ -32,8 +33,35 @@ class MLP(nn.Module):
                     self.mlp.append(nn.Dropout(dropout))
         self.mlp.append(L2NormalizationLayer() if normalize else nn.Identity())
 
+    # ---- reduced-precision path: bf16 tcgen05 GEMMs (csrc/gemm_tc.cu).  Opt-in and forward-only: chosen when no
+    # gradient is needed AND (self.precision == "bf16" OR a bf16 torch.autocast region is active -- the reference runs
+    # these Linears in bf16 under accelerator.autocast(), train_rqvae.py:36,69).  The default stays the exact fp32 GEMM.
+    precision = "fp32"
+
+    def _bf16_wanted(self, x: Tensor) -> bool:
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False
+        want = self.precision == "bf16" or (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+        dims = [self.input_dim] + list(self.hidden_dims) + [self.out_dim]
+        return bool(want) and x.is_cuda and ops.bf16_supported(dims)
+
+    def _weight_images(self, weights):
+        key = tuple((w.data_ptr(), w._version) for w in weights)
+        cache = getattr(self, "_wimg_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, [ops.to_bf16_image(w.detach()) for w in weights])
+            object.__setattr__(self, "_wimg_cache", cache)
+        return cache[1]
+
     def forward(self, x: Tensor) -> Tensor:
         assert x.shape[-1] == self.input_dim, f"Invalid input dim: Expected {self.input_dim}, found {x.shape[-1]}"
+        if self._bf16_wanted(x):
+            weights = [m.weight for m in self.mlp if isinstance(m, nn.Linear)]
+            lead = x.shape[:-1]
+            y = ops.mlp_forward_bf16(x.reshape(-1, self.input_dim), weights,
+                                     bool(getattr(self, "normalize", False)) or isinstance(self.mlp[-1], L2NormalizationLayer),
+                                     weight_images=self._weight_images(weights))
+            return y.reshape(*lead, self.out_dim)
         if self.dropout != 0 and self.training:
             raise NotImplementedError("MLP dropout > 0 in training is not built (no reference caller sets it)")
         weights = [m.weight for m in self.mlp if isinstance(m, nn.Linear)]

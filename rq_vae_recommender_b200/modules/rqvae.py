@@ -181,10 +181,18 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
         )
 
     @torch.no_grad()
-    def tokenize(self, x: Tensor) -> Tensor:
-        """sem_ids [B,L] only: what SemanticIdTokenizer consumes (semids.py:125), ids-only eval kernel."""
+    def tokenize(self, x: Tensor, mlp_precision: str = None) -> Tensor:
+        """sem_ids [B,L] only: what SemanticIdTokenizer consumes (semids.py:125), ids-only eval kernel.
+        ``mlp_precision="bf16"`` runs the encoder on the bf16 tcgen05 GEMMs (faster, NOT index-exact vs fp32)."""
         x = x.to(next(self.encoder.parameters()).dtype)
-        res = self.encode(x)
+        if mlp_precision is not None:
+            old, self.encoder.precision = self.encoder.precision, mlp_precision
+            try:
+                res = self.encode(x)
+            finally:
+                self.encoder.precision = old
+        else:
+            res = self.encode(x)
         return ops.rq_tokenize(res, [layer.codebook() for layer in self.layers])
 
     def forward(self, batch: SeqBatch, gumbel_t: float) -> RqVaeComputedLosses:

@@ -431,3 +431,58 @@ def rq_tokenize_tc(x: torch.Tensor, codebooks=None, state: Optional[TcState] = N
                                               _p(stats), _stream()), "tokenize_tc_run")
     _count(1)
     return ids
+
+
+# ---------------------------------------------------------------------------------------------- bf16 tensor-core MLP
+def bf16_supported(dims) -> bool:
+    """Every contraction dim (all but the last entry of [in, hidden..., out]) must be a multiple of 64."""
+    return all(d % 64 == 0 for d in dims[:-1])
+
+
+def to_bf16_image(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, K] -> bf16 operand image (csrc/gemm_tc.cu); used for activations and for weights W[N, K]."""
+    _need_cuda(x)
+    lib = _lib.load()
+    x = _rows(x)
+    rows, K = x.shape
+    nbytes = lib.rqb200_bf16_image_bytes(rows, K)
+    if nbytes == 0 and rows:
+        raise _lib.Rqb200Error(f"bf16 image needs K % 64 == 0, got K={K}")
+    img = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rqb200_f32_to_bf16_image(_p(x), x.stride(0), rows, K, _p(img), _stream()), "f32_to_bf16_image")
+    _count(1)
+    return img
+
+
+@torch.no_grad()
+def mlp_forward_bf16(x: torch.Tensor, weights: Sequence[torch.Tensor], normalize: bool = False,
+                     weight_images: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """modules/encoder.py:23-38 with bf16 tcgen05 GEMMs (fp32 accumulate, ReLU fused; activations stay in the bf16
+    operand-image layout between layers).  Forward only, reduced precision: NOT index-exact vs the fp32 reference."""
+    _need_cuda(x, *weights)
+    lib = _lib.load()
+    x = _rows(x)
+    M = x.shape[0]
+    dims = [x.shape[1]] + [w.shape[0] for w in weights]
+    if not bf16_supported(dims):
+        raise _lib.Rqb200Error(f"bf16 MLP needs every contraction dim to be a multiple of 64, got {dims}")
+    if weight_images is None:
+        weight_images = [to_bf16_image(w.detach()) for w in weights]
+    a = to_bf16_image(x)
+    n = len(weights)
+    out = None
+    with torch.cuda.device(x.device):
+        for i, (w, wi) in enumerate(zip(weights, weight_images)):
+            N, K = w.shape
+            last = i == n - 1
+            nxt = None
+            if not last:
+                nxt = torch.empty(lib.rqb200_bf16_image_bytes(M, N), dtype=torch.uint8, device=x.device)
+            else:
+                out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            _lib.check(lib.rqb200_gemm_bf16(_p(a), _p(wi), M, N, K, int(not last), _p(nxt), _p(out) if last else 0,
+                                            N if last else 0, _stream()), "gemm_bf16")
+            _count(1)
+            a = nxt
+    return l2norm_rows(out) if normalize else out

@@ -246,3 +246,34 @@ def test_training_loop_like_train_rqvae():
     assert usage.shape == (3, 256) and usage.sum(1).tolist() == [N] * 3
     _, counts = torch.unique(corpus[:, :-1], dim=0, return_counts=True)        # train_rqvae.py:279-283
     assert counts.max().item() - 1 == corpus[:, -1].max().item()
+
+
+def test_mlp_bf16_path_is_opt_in_and_forward_only():
+    """precision="bf16" / bf16 autocast selects the tcgen05 GEMMs only when no gradient is needed; default stays exact."""
+    from rq_vae_recommender_b200.modules.encoder import MLP
+    torch.manual_seed(0)
+    mlp = MLP(input_dim=768, hidden_dims=[512, 256, 128], out_dim=32).cuda()
+    x = dev(I.unit_rows(3, 500, 768))
+    ws = [host(m.weight) for m in mlp.mlp if isinstance(m, torch.nn.Linear)]
+    exact = mlp(x)                                           # grad enabled, params require grad -> exact fp32 path
+    assert exact.requires_grad and rel_err(host(exact), O.mlp_forward(host(x), ws)) < 1e-5
+    with torch.no_grad():
+        assert torch.equal(mlp(x), exact.detach())           # default precision: still exact
+        mlp.precision = "bf16"
+        y16 = mlp(x)
+        ref16 = O.mlp_forward_bf16(host(x), ws)
+        err = np.abs(host(y16).astype(np.float64) - ref16) / np.abs(ref16).max()
+        assert np.median(err) < 1e-6 and err.max() < 1e-2
+        assert not torch.equal(y16, exact.detach())
+        y16b = mlp(x)
+        assert torch.equal(y16, y16b)                        # weight-image cache reused, deterministic
+        mlp.mlp[0].weight.mul_(1.5)                          # in-place update bumps _version -> cache rebuilt
+        assert not torch.equal(mlp(x), y16)
+    mlp.precision = "fp32"
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = mlp(x)                                          # bf16 autocast region (the reference's AMP mode) -> bf16 GEMMs
+    with torch.no_grad():
+        mlp.precision = "bf16"
+        assert torch.equal(ya, mlp(x))
+    mlp.precision = "bf16"
+    assert mlp(x).requires_grad                              # gradient needed -> falls to the exact, differentiable path
