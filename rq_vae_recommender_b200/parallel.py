@@ -97,17 +97,23 @@ class CorpusTokenizer:
 
     def measured_traffic_bytes(self):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the 65 536 x 768 bench shape,
-        from the committed `ncu --set full` capture (profiles/); None when no capture covers the active kernel."""
+        from the committed `ncu --set full` capture of the shipped kernel (profiles/r1_tc_final_summary.csv); None when no
+        capture covers the active kernel."""
         import csv
         import os
         if not self.use_tc:
             return None
         path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
-                            "r1_prof_tc_r1e_summary.csv")
+                            "r1_tc_final_summary.csv")
         try:
-            vals = {r[0]: (r[1], float(r[2])) for r in csv.reader(open(path)) if len(r) == 3 and r[0].startswith("dram__bytes")}
+            rows = list(csv.reader(open(path)))
+            hdr, units, vals = rows[0], rows[1], rows[2]
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            return int(sum(v * scale[u] for u, v in vals.values()))
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                tot += float(vals[i]) * scale[units[i]]
+            return int(tot)
         except Exception:
             return None
 
