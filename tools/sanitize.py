@@ -1,0 +1,30 @@
+"""Small-shape pass over every kernel family for compute-sanitizer memcheck."""
+import sys, numpy as np, torch
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+import inputs as I
+from rq_vae_recommender_b200 import ops
+from rq_vae_recommender_b200.init.kmeans import Kmeans
+def dev(a): return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+# fused chain fwd (all modes, ragged shapes) + bwd
+for (B, D, K, L) in [(37, 20, 5, 3), (130, 64, 256, 3), (65, 768, 256, 3)]:
+    x, cbs = I.rq_problem(max(B, K), D, K, L, seed=B); x = x[:B]
+    for mode in (0, 2, 3):
+        xt = dev(x).requires_grad_(True); cts = [dev(c).requires_grad_(True) for c in cbs]
+        a, b, ids, loss = ops.RqChainFunction.apply(xt, mode, 0.25, False, *cts)
+        (a.sum() + b.sum() + loss.sum()).backward()
+# tc tokeniser: partial last tile, several tiles, L=1 and L=4
+for (B, D, L) in [(1, 768, 3), (129, 768, 3), (300, 64, 1), (513, 256, 4)]:
+    x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D); x = x[:B]
+    st = torch.zeros(64, dtype=torch.int32, device='cuda')
+    ops.rq_tokenize_tc(dev(x), [dev(c) for c in cbs], stats=st)
+# gumbel level fwd/bwd, mlp fwd/bwd, kmeans, histogram
+x, cbs = I.rq_problem(300, 32, 256, 1, seed=3)
+xt = dev(x).requires_grad_(True); ct = dev(cbs[0]).requires_grad_(True)
+e, ids, loss = ops.GumbelQuantizeFunction.apply(xt, ct, dev(I.rand(4, 300, 256)), 0.2, 0.25); (e.sum() + loss.sum()).backward()
+ws = [dev(w).requires_grad_(True) for w in I.mlp_weights(5, [70, 33, 17])]
+xm = dev(I.randn(6, 45, 70)).requires_grad_(True)
+ops.MLPFunction.apply(xm, True, *ws).sum().backward()
+np.random.seed(0); torch.manual_seed(0)
+Kmeans(k=16, max_iters=3).run(dev(I.randn(7, 500, 12)))
+ops.sid_histogram(torch.randint(0, 256, (1000, 3), device='cuda'), 256)
+torch.cuda.synchronize(); print("sanitize pass done")
