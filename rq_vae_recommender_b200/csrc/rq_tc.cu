@@ -635,9 +635,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const bool many = flagged && !(m3 > thr);           // >= 3 candidates: rare, needs the full candidate mask
         const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
         const uint32_t mn = __ballot_sync(0xffffffffu, many);
+        // candidate bitmask of the rows with >= 3 candidates.  It lives in local memory (dynamically indexed) = L2 here,
+        // so it is only touched on that rare path: every word is written inside `if (mn)` before the re-rank reads it.
         uint32_t mask[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mask[c] = 0;
         TC_ACC(e_merge, te);
         if (mn) {
           // second pass over all 256 scores (warp-uniform branch): exact candidate bitmask for the `many` rows
