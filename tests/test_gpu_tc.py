@@ -97,3 +97,28 @@ def test_tc_strided_rows_and_state_reuse(ops):
     b = ops.rq_tokenize_tc(dev(x), state=state).cpu().numpy()
     assert np.array_equal(a, b)
     assert_ids_match(b, O.rq_tokenize(x, cbs), x, cbs)
+
+
+def test_tc_misaligned_rows_take_the_scalar_load_path(ops):
+    """x whose base is not 16-byte aligned (and whose row stride is not a multiple of 4) -> the converter's scalar loads."""
+    D, K, L = 128, 256, 3
+    x, cbs = I.rq_problem(1024, D, K, L, seed=33)
+    big = torch.zeros(700, D + 7, device="cuda")
+    big[:, 3:3 + D] = dev(x[:700])
+    view = big[:, 3:3 + D]                         # offset 3 floats, row stride D+7
+    assert view.data_ptr() % 16 != 0 and view.stride(0) % 4 != 0
+    a = ops.rq_tokenize_tc(view, [dev(c) for c in cbs]).cpu().numpy()
+    b = ops.rq_tokenize_tc(dev(x[:700]), [dev(c) for c in cbs]).cpu().numpy()
+    assert np.array_equal(a, b)
+    assert_ids_match(b, O.rq_tokenize(x[:700], cbs), x[:700], cbs)
+
+
+def test_tc_max_levels(ops):
+    """L = 8 (RQB_MAX_LEVELS): 28 Gram tables, the serial j >= 2 correction path, all 8 bytes of the packed ids."""
+    D, K, L = 64, 256, 8
+    x, cbs = I.rq_problem(1024, D, K, L, seed=44)
+    ids, stats = run_tc(ops, x[:600], cbs)
+    assert ids.shape == (600, 8)
+    n_tie = assert_ids_match(ids, O.rq_tokenize(x[:600], cbs), x[:600], cbs, "tc L=8")
+    assert n_tie <= 2
+    assert not ops.tc_supported(64, 256, 9)
