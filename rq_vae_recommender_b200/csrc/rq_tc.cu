@@ -8,16 +8,22 @@
 //   S_l[b,k]  = fp16(x_b) . fp16(c_{l,k})            (tcgen05.mma, fp32 accumulate in TMEM; exact power-of-two scales)
 //   score_l   = cc_{l,k} - 2 (S_l - sum_{j<l} G_{jl}[id_j, k])     (G = fp32 Gram tables C_j C_l^T, so every level is
 //               scored from the ONE fp16 image of x: the residual never has to be re-quantised or re-staged)
-//   candidates = { k : score <= min + 4 eps_b }      eps_b bounds the fp16 rounding of the dot product (see tc_margin)
+//   candidates = { k : score <= min + 4 eps_b }      eps_b bounds the fp16 rounding of the dot product (margin in the epilogue)
 //   |candidates| == 1  -> that code is the exact argmin;  else the candidates are re-scored with the exact fp32
 //   arithmetic of the CUDA-core kernel (sequential fp32 residual, (xx + cc) - 2 dot, first index wins ties).
 //
-// Kernel structure (persistent, one CTA per SM, 128 rows per tile, warp specialised):
-//   warp 0       B producer  : 16 KB pre-swizzled fp16 codebook blocks -> smem ring, TMA bulk copies + mbarriers
-//   warp 1       MMA issuer  : one thread issues tcgen05.mma (M128 N128 K16), accumulators double-buffered in TMEM
-//   warps 2-9    converters  : 128-bit coalesced fp32 loads of x -> fp16 -> K-major SWIZZLE_128B smem (A operand),
-//                              refilled chunk by chunk as the last level releases it (x is read from HBM once)
-//   warps 10-13  epilogue    : tcgen05.ld scores, Gram correction, candidate detection, warp-cooperative exact re-rank
+// Kernel structure (persistent, one CTA per SM, 128 rows per tile, 16 warps = 4 warpgroups, setmaxnreg 32 / 128 / 176):
+//   WG0 warp 0   B producer  : 16 KB pre-swizzled fp16 codebook blocks -> 2-stage smem ring, TMA bulk copies + mbarriers
+//   WG0 warp 1   MMA issuer  : one thread issues tcgen05.mma (M128 N128 K16), chunk-major (k chunk outer, column half
+//                              inner), accumulators double-buffered in TMEM (2 x 256 columns)
+//   WG1 (4 warps) converters : 128-bit coalesced fp32 loads of x -> fp16 -> K-major SWIZZLE_128B smem (A operand),
+//                              refilled chunk by chunk as the last level releases it (x is read from HBM once);
+//                              also the per-row max|x| and sum x^2 the filter margin needs
+//   WG2-3 (8 warps) epilogue : 2 warps per TMEM lane quarter (one per 128-column half): tcgen05.ld scores, Gram
+//                              correction, top-3 candidates, merge through smem, warp-cooperative exact re-rank
+// With the 225 KB shared-memory carve-out there is no L1, so a register spill is an L2 round trip: the hot loops are kept
+// spill-free (checked in SASS) and the role budgets sum to the CTA's launch allocation (setmaxnreg draws from it).
+// Measured limits and the hypotheses tested on the way: DESIGN.md section 5.2, profiles/r1_tc_role_trace.txt.
 #include "common.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
