@@ -44,7 +44,11 @@ extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float a
 #define TC_NCONV_WARPS 4
 #define TC_NEPI_WARPS 8
 #define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 4 converters | 8 epilogue (2 per TMEM lane quarter) = 512 threads
-#define TC_Z 6.0f         // margin multiplier on the statistical fp16 rounding bound
+// Margin multiplier on the statistical fp16 rounding bound sigma' (DESIGN.md "filter error bound").  Validated with the
+// sum-x^4 statistic at z = 6 (worst observed error 2.3 sigma' over 12.6 M pairs).  The cheaper statistic now in use,
+// sum x^4 <= max|x|^2 sum x^2, makes sigma' ~1.38x larger on gaussian-like rows, so z = 6 / 1.38 keeps the SAME
+// effective margin that was validated instead of an accidentally wider one (which only adds re-rank work).
+#define TC_Z 4.5f
 
 struct TcLevelConst {
   float sc;      // power-of-two scale applied to the codebook before fp16 conversion
