@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #define RQ_THREADS 256
 #define RQ_BK 16
@@ -524,7 +525,14 @@ static size_t fused_smem_bytes(int tm, int tn, int Dp) {
 }
 
 static int pick_tm(int B, int tn, int Dp) {
-  int tm = 8;
+  if (const char* e = getenv("RQB200_TM")) {     // tuning knob: force the row-tile height (8, 4, 2 or 1)
+    const int f = atoi(e);
+    if ((f == 8 || f == 4 || f == 2 || f == 1) && fused_smem_bytes(f, tn, Dp) <= 200 * 1024) return f;
+  }
+  // Measured on B200 (tools/rq_tm_sweep.py, K=256, L=3): with a short K loop (D <= 64: at most 4 chunks per level) the
+  // 8x8 register tile costs occupancy (168 regs -> one CTA per SM) without paying back in FMA efficiency; TM=4 is 15 %
+  // faster at D=32 and 8 % at D=64, equal at D=128, and TM=2/1 are slower everywhere.
+  int tm = (Dp <= 64) ? 4 : 8;
   while (tm >= 1 && fused_smem_bytes(tm, tn, Dp) > 200 * 1024) tm >>= 1;
   if (tm < 1) return 0;
   while (tm > 1 && (B + 8 * tm - 1) / (8 * tm) < 148) tm >>= 1;
