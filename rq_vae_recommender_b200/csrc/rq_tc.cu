@@ -20,11 +20,16 @@
 //                              refilled chunk by chunk as the last level releases it (x is read from HBM once);
 //                              also the per-row max|x| and sum x^2 the filter margin needs
 //   WG2-3 (8 warps) epilogue : 2 warps per TMEM lane quarter (one per 128-column half): tcgen05.ld scores, Gram
-//                              correction, top-3 candidates, merge through smem, warp-cooperative exact re-rank
+//                              correction, packed-key top-3 (tc_select.cuh), merge through smem, warp-cooperative
+//                              exact re-rank from the fp32 codebook copy held in the prepared state
+// Hot loops are kept SMALL on purpose (16-column rolled scan body, vector-only converter instantiation): the first
+// versions were 100+ KB of straight-line SASS and ncu showed `no_inst` (instruction fetch) as the top stall of plain ALU
+// instructions -- the L1.5 instruction cache is 32 KB, the per-scheduler L0 ~6 KB.
 // With the 225 KB shared-memory carve-out there is no L1, so a register spill is an L2 round trip: the hot loops are kept
 // spill-free (checked in SASS) and the role budgets sum to the CTA's launch allocation (setmaxnreg draws from it).
 // Measured limits and the hypotheses tested on the way: DESIGN.md section 5.2, profiles/r1_tc_role_trace.txt.
 #include "common.cuh"
+#include "tc_select.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
@@ -71,7 +76,8 @@ static size_t tc_off_cc(int L) { return rqb_round_up(sizeof(TcHeader), 256); }
 static size_t tc_off_hcc(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
 static size_t tc_off_gram(int L) { return tc_off_hcc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
 static size_t tc_off_cbptr(int L) { return tc_off_gram(L) + (size_t)(L * (L - 1) / 2) * TC_K * TC_K * 4; }
-static size_t tc_off_blob(int L) { return rqb_round_up(tc_off_cbptr(L) + RQB_MAX_LEVELS * 8, 1024); }
+static size_t tc_off_cbf(int L) { return rqb_round_up(tc_off_cbptr(L) + RQB_MAX_LEVELS * 8, 256); }   // fp32 copy [L][256][D]
+static size_t tc_off_blob(int D, int L) { return rqb_round_up(tc_off_cbf(L) + (size_t)L * TC_K * D * 4, 1024); }
 
 extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) {
   return (K == TC_K && D >= TC_KC && D <= TC_MAX_D && D % TC_KC == 0 && L >= 1 && L <= RQB_MAX_LEVELS) ? 1 : 0;
@@ -79,7 +85,7 @@ extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) {
 
 extern "C" size_t rqb200_tokenize_tc_state_bytes(int D, int K, int L) {
   if (!rqb200_tokenize_tc_supported(D, K, L)) return 0;
-  return tc_off_blob(L) + (size_t)L * 2 * (D / TC_KC) * TC_BSTAGE_BYTES;
+  return tc_off_blob(D, L) + (size_t)L * 2 * (D / TC_KC) * TC_BSTAGE_BYTES;
 }
 
 // ------------------------------------------------------------------------------------------------ prepare
@@ -176,9 +182,14 @@ extern "C" int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, 
   float* cc = reinterpret_cast<float*>(base + tc_off_cc(L));
   float* gram = reinterpret_cast<float*>(base + tc_off_gram(L));
   const float** cbptr = reinterpret_cast<const float**>(base + tc_off_cbptr(L));
-  __half* blob = reinterpret_cast<__half*>(base + tc_off_blob(L));
+  __half* blob = reinterpret_cast<__half*>(base + tc_off_blob(D, L));
+  float* cbf = reinterpret_cast<float*>(base + tc_off_cbf(L));
   RQB_CUDA(cudaMemsetAsync(hdr, 0, sizeof(TcHeader), st));
   RQB_CUDA(cudaMemcpyAsync(cbptr, codebooks, sizeof(float*) * L, cudaMemcpyHostToDevice, st));
+  // fp32 copy for the exact re-rank: 256-byte aligned rows whatever the caller's tensors look like, and the prepared state
+  // no longer references caller memory after this call returns (stream order)
+  for (int l = 0; l < L; ++l)
+    RQB_CUDA(cudaMemcpyAsync(cbf + (size_t)l * TC_K * D, codebooks[l], sizeof(float) * TC_K * D, cudaMemcpyDeviceToDevice, st));
   tc_prep_stats_kernel<<<dim3(TC_K / 8, L), 256, 0, st>>>(cbptr, D, hdr, cc);
   RQB_LAUNCH_CHECK();
   tc_prep_consts_kernel<<<1, 32, 0, st>>>(hdr, L);
@@ -266,7 +277,7 @@ struct TcParams {
   const float* cc;      // [L][256]
   const float* hcc;     // [L][256]  cc / 2
   const float* gram;    // [L(L-1)/2][256][256]
-  const float* const* cb;  // device array of L fp32 codebook pointers (exact re-rank)
+  const float* cbf;     // [L][256][D] fp32 codebook copy (exact re-rank), rows 256-byte aligned
   const unsigned char* blob;
   int64_t* ids;         // [B][L]
   int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
@@ -308,18 +319,24 @@ __device__ __forceinline__ uint32_t tc_bf16_up(float v) {   // bf16 bits of the 
   return b >> 16;
 }
 
-// branch-free insertion of (a, k) into the sorted top-3 values / top-2 indices; strict '<' keeps the earlier index
-__device__ __forceinline__ void tc_insert(float a, int k, float& m1, float& m2, float& m3, int& i1, int& i2) {
-  const bool lt1 = a < m1, lt2 = a < m2;
-  m3 = fminf(m3, fmaxf(m2, a));
-  m2 = fminf(m2, fmaxf(m1, a));
-  m1 = fminf(m1, a);
-  i2 = lt1 ? i1 : (lt2 ? k : i2);
-  i1 = lt1 ? k : i1;
+// 16 consecutive fp32 columns of this thread's TMEM lane (row); asynchronous until tc_ld_wait()
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 
-// kTrace = true compiles the clock64 role accounting in (RQB200_TC_TRACE=1); the production instantiation carries none of it
-template <bool kTrace>
+__device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
+
+// kTrace = true compiles the clock64 role accounting in (RQB200_TC_TRACE=1); the production instantiation carries none of it.
+// kVec = false is the slow-path instantiation for x whose rows are not 16-byte aligned (scalar loads); keeping it out of the
+// main instantiation halves the converter's code.
+template <bool kTrace, bool kVec>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
@@ -418,13 +435,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     // (stays at the launch allocation of 128 registers: at 96 this loop spilled its row pointers -> L2 latency per chunk)
     const int cw = warp - 4;
     const int rsub = lane >> 3, q8 = lane & 7;
-    const bool vec_ok = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
     uint32_t it = 0;
     long long c_wait = 0, c_work = 0, c_ldwait = 0, c_cvt = 0;
     TC_T0(tcv);
     const long long tcv_start = tcv;
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int row_base = tile * TC_BM + cw * 32 + rsub;
       // row statistics for the filter margin: max|x| and sum x^2 (sum x^4 <= max|x|^2 * sum x^2 is used downstream; max|x|
       // doubles as the fp16 overflow test, NaN inputs surface through sum x^2).  ~half the ALU of tracking sum x^4 and
       // testing every converted half for inf.
@@ -432,23 +448,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { sm[i] = 0.f; s2[i] = 0.f; }
       float4 va[8], vb[8];
-      // half-unit h: chunk kc = h >> 1, float4 columns 8*(h & 1) + q8, rows row_base + 4i.
-      // Register-frugal on purpose (a spill here is an L2 round trip per chunk): ONE 64-bit base pointer, the row
-      // stride, and compile-time multiples of it; shared-memory offsets are one base plus immediates -- the swizzle term
-      // (chunk ^ (row & 7)) only depends on the parity of i because rows advance by 4.
-      const float* xrow = p.x + (int64_t)row_base * p.ldx + q8 * 4;     // row_base + 0, float4 column q8
-      const int nvalid = p.B - row_base;                                 // row 4i is valid iff 4i < nvalid
-      const int64_t stride4 = 4 * p.ldx;
+      // half-unit h: chunk kc = h >> 1, float4 columns 8*(h & 1) + q8 (= element 32 h + 4 q8 of the row), rows row_base + 4i.
+      // Register- and instruction-frugal on purpose: ONE 64-bit tile pointer plus eight 32-bit row offsets.  Rows past B
+      // are CLAMPED to row B-1 instead of predicated: no zero-fill, no per-load compare, one code path; their scores are
+      // never stored.  (host side guarantees 127 * ldx < 2^32)
+      const float* xt = p.x + (int64_t)tile * TC_BM * p.ldx + q8 * 4;
+      const int last = p.B - 1 - tile * TC_BM;                           // >= 0: last valid row of this tile
+      uint32_t off[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) off[i] = (uint32_t)min(cw * 32 + rsub + 4 * i, last) * (uint32_t)p.ldx;
       auto load_half = [&](float4 (&v)[8], int h) {
-        const float* src0 = xrow + (h >> 1) * TC_KC + (h & 1) * 32;
+        const float* xh = xt + h * 32;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (4 * i < nvalid) {
-            const float* src = src0 + i * stride4;
-            if (vec_ok) v[i] = ldg_stream(reinterpret_cast<const float4*>(src));
-            else { v[i].x = __ldg(src); v[i].y = __ldg(src + 1); v[i].z = __ldg(src + 2); v[i].w = __ldg(src + 3); }
-          }
+          const float* src = xh + off[i];
+          if (kVec) v[i] = ldg_stream(reinterpret_cast<const float4*>(src));
+          else { v[i].x = __ldg(src); v[i].y = __ldg(src + 1); v[i].z = __ldg(src + 2); v[i].w = __ldg(src + 3); }
         }
       };
       const uint32_t srow = (uint32_t)(cw * 32 + rsub) * 128;            // byte offset of row (cw*32 + rsub) in a chunk
@@ -523,27 +538,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_x = 2 + quarter;      // half 1 -> half 0: exch[] written
     const int bar_i = 6 + quarter;      // half 0 -> half 1: the level's id is final (written into exch[].idx)
+    const int D = p.D;
+    const int lane4 = lane * 4;
     uint32_t g = 0, it = 0;
     long long e_tf = 0, e_scan = 0, e_pair = 0, e_rr = 0, e_idw = 0, e_merge = 0, e_many = 0;
     TC_T0(te);
     const long long te_start = te;
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int row = tile * TC_BM + r_local;
-      const bool valid = row < p.B;
+      const bool valid = row < p.B;    // rows past B run the same code on zero scores (no divergent copies); nothing of theirs is stored
       uint64_t idpack = 0;          // 8 bits per level
       float x4s = 0.f, x2s = 0.f;
+#pragma unroll 1
       for (int l = 0; l < L; ++l, ++g) {
         const uint32_t buf = g & 1, u = g >> 1;
-        const TcLevelConst lc = p.hdr->lv[l];
-        // T rows: hcc (level 0, shared by all rows) or the Gram rows of the codes chosen at levels j < l (cc/2 folded in j=0)
-        const float* trow0 = p.hcc + half * 128;
-        const float* trow1 = trow0;
-        if (l >= 1) trow0 = p.gram + ((size_t)(l * (l - 1) / 2 + 0) * TC_K + (size_t)(idpack & 0xff)) * TC_K + half * 128;
-        if (l >= 2) trow1 = p.gram + ((size_t)(l * (l - 1) / 2 + 1) * TC_K + (size_t)((idpack >> 8) & 0xff)) * TC_K + half * 128;
+        // T rows (full 256-column rows): hcc at level 0, else the Gram rows of the codes chosen at levels j < l, with cc/2
+        // folded into table j = 0.  Two rows are pipelined statically (L <= 3 is the fast path); rows j >= 2 are summed in.
+        const int tri = l * (l - 1) / 2;
+        auto grow = [&](int j) -> const float* {
+          return p.gram + ((size_t)(tri + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K;
+        };
+        const float* trow0 = (l >= 1) ? grow(0) : p.hcc;
+        const float* trow1 = (l >= 2) ? grow(1) : trow0;
+        auto load_t = [&](float4 (&ta)[4], float4 (&tb)[4], int col) {      // issue only: nothing here waits for data
+#pragma unroll
+          for (int v = 0; v < 4; ++v) ta[v] = __ldg(reinterpret_cast<const float4*>(trow0 + col) + v);
+          if (l >= 2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) tb[v] = __ldg(reinterpret_cast<const float4*>(trow1 + col) + v);
+          }
+        };
+        auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {   // called one chunk of compute after load_t
+          if (l >= 2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
+#pragma unroll 1
+            for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
+              const float4* gj = reinterpret_cast<const float4*>(grow(j) + col);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const float4 t = __ldg(gj + v);
+                ta[v].x += t.x; ta[v].y += t.y; ta[v].z += t.z; ta[v].w += t.w;
+              }
+            }
+          }
+        };
+        const int col0 = half * 128;
+        float4 ta0[4], tb0[4], ta1[4], tb1[4];
+        load_t(ta0, tb0, col0);          // in flight across the accumulator wait below
         TC_ACC(e_rr, te);
         mbar_wait_guarded(&ms->t_full[buf][half], u & 1, 7);
         TC_ACC(e_tf, te);
         tc_fence_after();
+        const uint32_t tcol = TC_TMEM_BASE() + lane_addr + buf * 256 + col0;
+        uint32_t s0[16], s1[16];
+        tc_ld16_issue(tcol, s0);
+        const TcLevelConst lc = p.hdr->lv[l];
         if (l == 0 && half == 0) {       // only the merging warp needs the margin
           const uint32_t ri = ms->rowinfo[r_local];
           const float xmax = __uint_as_float(ri & 0xffff0000u);        // max|x| (bf16, rounded up)
@@ -559,70 +610,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float eps = TC_Z * sig + flo + acc + lc.gerr;
         const float margin = 2.f * eps;
         const float ninv = -1.f / (p.sx * lc.sc);
-        const uint32_t tcol = TC_TMEM_BASE() + lane_addr + buf * 256 + half * 128;
 
         float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
         int i1 = 0, i2 = 0;
-        // T rows for one 32-column chunk: all loads of the chunk issued back to back (<= 16 x LDG.128 in flight)
-        auto load_t = [&](float4 (&ta)[8], int c) {
-          if (valid) {
+        // one 16-column chunk: packed-key triple (7 instructions per score), then one merge into the running top-3
+        auto score16 = [&](const uint32_t (&s)[16], const float4 (&t)[4], int col) {
+          float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
 #pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = __ldg(reinterpret_cast<const float4*>(trow0 + c * 32) + v4);
-            if (l >= 2) {
-              float4 tb[8];
-#pragma unroll
-              for (int v4 = 0; v4 < 8; ++v4) tb[v4] = __ldg(reinterpret_cast<const float4*>(trow1 + c * 32) + v4);
-#pragma unroll
-              for (int v4 = 0; v4 < 8; ++v4) { ta[v4].x += tb[v4].x; ta[v4].y += tb[v4].y; ta[v4].z += tb[v4].z; ta[v4].w += tb[v4].w; }
-            }
-            for (int j = 2; j < l; ++j) {   // L > 3 only
-              const float* gj = p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + half * 128 + c * 32;
-#pragma unroll
-              for (int v4 = 0; v4 < 8; ++v4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(gj) + v4);
-                ta[v4].x += t.x; ta[v4].y += t.y; ta[v4].z += t.z; ta[v4].w += t.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) ta[v4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int v = 0; v < 4; ++v) {
+            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
+            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
+            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
+            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
           }
+          tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
         };
-        auto score_chunk = [&](const float4 (&ta)[8], int c) {
-          uint32_t sr[32];
-          tc_ld32_issue(tcol + c * 32, sr);
-          tc_ld_wait();
-          if (valid) {
-            // chunk-local top-3 with immediate indices, then one merge into the running top-3
-            float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
-            int j1 = 0, j2 = 0;
-#pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) {
-              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 0]), ninv, ta[v4].x), v4 * 4 + 0, q1, q2, q3, j1, j2);
-              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 1]), ninv, ta[v4].y), v4 * 4 + 1, q1, q2, q3, j1, j2);
-              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 2]), ninv, ta[v4].z), v4 * 4 + 2, q1, q2, q3, j1, j2);
-              tc_insert(fmaf(__uint_as_float(sr[v4 * 4 + 3]), ninv, ta[v4].w), v4 * 4 + 3, q1, q2, q3, j1, j2);
-            }
-            const int kb = half * 128 + c * 32;
-            tc_insert(q1, kb + j1, m1, m2, m3, i1, i2);
-            tc_insert(q2, kb + j2, m1, m2, m3, i1, i2);
-            m3 = fminf(m3, fmaxf(m2, q3)); // q3 >= q2: it can only displace m3
-          }
-        };
-        {
-          // software pipeline over the 4 chunks: the next chunk's Gram rows are in flight while this one is scored.
-          // Rolled into two iterations of a two-chunk body (same prefetch distance): the fully unrolled form was ~54 KB
-          // of SASS and ncu showed 26 % `no_inst` (instruction-cache) stalls in this region.
-          float4 t0[8], t1[8];
-          load_t(t0, 0);
+        fold_t(ta0, tb0, col0);
+        // software pipeline, two chunks per trip: the next chunk's Gram rows and TMEM columns are in flight while this one
+        // is scored.  The body is ~400 instructions on purpose (see the instruction-cache note in the file header).
 #pragma unroll 1
-          for (int c = 0; c < 4; c += 2) {
-            load_t(t1, c + 1);
-            score_chunk(t0, c);
-            if (c + 2 < 4) load_t(t0, c + 2);
-            score_chunk(t1, c + 1);
-          }
+        for (int c = 0; c < 128; c += 32) {
+          load_t(ta1, tb1, col0 + c + 16);
+          tc_ld_wait();                                   // s0 landed
+          tc_ld16_issue(tcol + c + 16, s1);
+          score16(s0, ta0, col0 + c);
+          fold_t(ta1, tb1, col0 + c + 16);
+          const bool more = c + 32 < 128;                 // warp-uniform
+          if (more) load_t(ta0, tb0, col0 + c + 32);
+          tc_ld_wait();                                   // s1 landed
+          if (more) tc_ld16_issue(tcol + c + 32, s0);
+          score16(s1, ta1, col0 + c + 16);
+          if (more) fold_t(ta0, tb0, col0 + c + 32);
         }
+        tc_ld_wait();
 
         TC_ACC(e_scan, te);
         if (half == 1) {
@@ -646,7 +666,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           tc_insert(e.m2, (int)((e.idx >> 8) & 0xff), m1, m2, m3, i1, i2);
           m3 = fminf(m3, fmaxf(m2, e.m3));
         }
-        const float thr = m1 + margin;
+        const float thr = tcs_threshold(m1, margin);
         const bool flagged = valid && !(m2 > thr);          // >= 2 candidates (NaN/inf margins land here too)
         const bool many = flagged && !(m3 > thr);           // >= 3 candidates: rare, needs the full candidate mask
         const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
@@ -656,28 +676,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         uint32_t mask[8];
         TC_ACC(e_merge, te);
         if (mn) {
-          // second pass over all 256 scores (warp-uniform branch): exact candidate bitmask for the `many` rows
+          // second pass over all 256 raw scores (warp-uniform branch): exact candidate bitmask for the `many` rows
           const uint32_t tall = TC_TMEM_BASE() + lane_addr + buf * 256;
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            uint32_t sr[32];
-            tc_ld32_issue(tall + c * 32, sr);
-            tc_ld_wait();
+          for (int w = 0; w < 8; ++w) {
             uint32_t mw = 0;
-            if (many) {
 #pragma unroll 1
-              for (int e = 0; e < 32; ++e) {
-                const int k = c * 32 + e;
-                float t = (l == 0) ? __ldg(p.hcc + k) : 0.f;
-                for (int j = 0; j < l; ++j)
-                  t += __ldg(p.gram + ((size_t)(l * (l - 1) / 2 + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K + k);
-                float sv = 0.f;
+            for (int hh = 0; hh < 2; ++hh) {
+              const int col = w * 32 + hh * 16;
+              tc_ld16_issue(tall + col, s0);
+              load_t(ta0, tb0, col);
+              fold_t(ta0, tb0, col);
+              tc_ld_wait();
+              uint32_t bits = 0;
 #pragma unroll
-                for (int tt = 0; tt < 32; ++tt) if (tt == e) sv = __uint_as_float(sr[tt]);
-                if (!(fmaf(sv, ninv, t) > thr)) mw |= 1u << e;
+              for (int v = 0; v < 4; ++v) {
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 0]), ninv, ta0[v].x) > thr)) << (v * 4 + 0);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 1]), ninv, ta0[v].y) > thr)) << (v * 4 + 1);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 2]), ninv, ta0[v].z) > thr)) << (v * 4 + 2);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 3]), ninv, ta0[v].w) > thr)) << (v * 4 + 3);
               }
+              mw |= bits << (hh * 16);
             }
-            mask[c] = mw;
+            mask[w] = mw;
           }
         }
         TC_ACC(e_many, te);
@@ -685,10 +706,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         mbar_arrive(&ms->t_empty[buf]);     // accumulator buffer may be overwritten by level l+2
 
         int my_id = i1;
-        // ---- warp-cooperative exact re-rank of the flagged rows (same arithmetic as rq_simt.cu)
+        // ---- warp-cooperative exact re-rank of the flagged rows (same arithmetic as rq_simt.cu: sequential fp32 residual,
+        // (xx + cc) - 2 dot, first index wins ties).  Lane covers elements 128 i + 4 lane .. +3 of a row (6 x LDG.128 per
+        // row); the x row, the first prior code and both candidates are all in flight together.
         const float* ccl = p.cc + l * TC_K;
+        const float* cl = p.cbf + (size_t)l * TC_K * D;
         uint32_t todo = fl;
         int n_cand = 0;
+        auto ld_row = [&](const float* base, float4 (&v)[6]) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            v[i] = (i * 128 + lane4 < D) ? __ldg(reinterpret_cast<const float4*>(base + i * 128 + lane4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+#pragma unroll 1
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
@@ -698,35 +728,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           const uint64_t rid = ((uint64_t)idhi << 32) | idlo;
           const int ci1 = __shfl_sync(0xffffffffu, i1, src), ci2 = __shfl_sync(0xffffffffu, i2, src);
           const bool is_many = (mn >> src) & 1;
-          float res[TC_MAX_D / 32];
+          const int ka = min(ci1, ci2), kb = max(ci1, ci2);
+          float4 res[6], ev[6], va[6], vb[6];
           const float* xr = p.x + (int64_t)rrow * p.ldx;
+          if (kVec) ld_row(xr, res);
+          else {
 #pragma unroll
-          for (int i = 0; i < TC_MAX_D / 32; ++i) res[i] = (i * 32 < p.D) ? __ldg(xr + i * 32 + lane) : 0.f;
-          for (int j = 0; j < l; ++j) {
-            const float* e = p.cb[j] + (int64_t)((rid >> (8 * j)) & 0xff) * p.D;
+            for (int i = 0; i < 6; ++i) {
+              res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (i * 128 + lane4 < D) {
+                const float* q = xr + i * 128 + lane4;
+                res[i].x = __ldg(q); res[i].y = __ldg(q + 1); res[i].z = __ldg(q + 2); res[i].w = __ldg(q + 3);
+              }
+            }
+          }
+          ld_row(cl + (size_t)ka * D, va);
+          ld_row(cl + (size_t)kb * D, vb);
+#pragma unroll 1
+          for (int j = 0; j < l; ++j) {      // the j = 0 row is in flight together with x and both candidates
+            ld_row(p.cbf + ((size_t)j * TC_K + (size_t)((rid >> (8 * j)) & 0xff)) * D, ev);
 #pragma unroll
-            for (int i = 0; i < TC_MAX_D / 32; ++i)
-              if (i * 32 < p.D) res[i] = res[i] - __ldg(e + i * 32 + lane);     // rqvae.py:130, level order
+            for (int i = 0; i < 6; ++i) { res[i].x -= ev[i].x; res[i].y -= ev[i].y; res[i].z -= ev[i].z; res[i].w -= ev[i].w; }   // rqvae.py:130, level order
           }
           float xx = 0.f;
 #pragma unroll
-          for (int i = 0; i < TC_MAX_D / 32; ++i) xx = fmaf(res[i], res[i], xx);
+          for (int i = 0; i < 6; ++i) xx = tc_dot4(res[i], res[i], xx);
           xx = warp_sum(xx);
-          const float* cl = p.cb[l];
           float best = INFINITY;
           int besti = 0x7fffffff;
           if (!is_many) {
-            // exactly two candidates: both dot products with all their loads in flight, ascending index order
-            const int ka = min(ci1, ci2), kb = max(ci1, ci2);
-            const float* pa = cl + (int64_t)ka * p.D;
-            const float* pb = cl + (int64_t)kb * p.D;
+            // exactly two candidates, ascending index order
             float da = 0.f, db = 0.f;
 #pragma unroll
-            for (int i = 0; i < TC_MAX_D / 32; ++i)
-              if (i * 32 < p.D) {
-                da = fmaf(res[i], __ldg(pa + i * 32 + lane), da);
-                db = fmaf(res[i], __ldg(pb + i * 32 + lane), db);
-              }
+            for (int i = 0; i < 6; ++i) { da = tc_dot4(res[i], va[i], da); db = tc_dot4(res[i], vb[i], db); }
             da = warp_sum(da);
             db = warp_sum(db);
             const float dist_a = (xx + __ldg(ccl + ka)) - 2.f * da;             // quantize.py:113-117
@@ -739,14 +773,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
               uint32_t mw = __shfl_sync(0xffffffffu, mask[c], src);
+#pragma unroll 1
               while (mw) {
                 const int k = c * 32 + __ffs(mw) - 1;
                 mw &= mw - 1;
-                const float* ck = cl + (int64_t)k * p.D;
+                ld_row(cl + (size_t)k * D, va);
                 float dot = 0.f;
 #pragma unroll
-                for (int i = 0; i < TC_MAX_D / 32; ++i)
-                  if (i * 32 < p.D) dot = fmaf(res[i], __ldg(ck + i * 32 + lane), dot);
+                for (int i = 0; i < 6; ++i) dot = tc_dot4(res[i], va[i], dot);
                 dot = warp_sum(dot);
                 const float dist = (xx + __ldg(ccl + k)) - 2.f * dot;
                 if (dist < best) { best = dist; besti = k; }
@@ -785,13 +819,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   }
 }
 
+template <bool kTrace, bool kVec>
+static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+  RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<kTrace, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rq_tc_kernel<kTrace, kVec><<<grid, TC_THREADS, smem, st>>>(p);
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}
+
 extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const void* state, int D, int K, int L,
                                       int64_t* ids, int* stats, void* stream) {
   if (!rqb200_tokenize_tc_supported(D, K, L)) {
     rqb_set_error("tokenize_tc: shape D=%d K=%d L=%d not supported", D, K, L);
     return RQB_ERR_UNSUPPORTED;
   }
-  RQB_CHECK_ARG(B >= 0 && ldx >= D, "tokenize_tc_run: bad shape");
+  RQB_CHECK_ARG(B >= 0 && ldx >= D && ldx < (1 << 24), "tokenize_tc_run: bad shape");
   if (B == 0) return RQB_OK;
   RQB_CHECK_ARG(x && state && ids, "tokenize_tc_run: null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -803,8 +845,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   p.cc = reinterpret_cast<const float*>(base + tc_off_cc(L));
   p.hcc = reinterpret_cast<const float*>(base + tc_off_hcc(L));
   p.gram = reinterpret_cast<const float*>(base + tc_off_gram(L));
-  p.cb = reinterpret_cast<const float* const*>(base + tc_off_cbptr(L));
-  p.blob = reinterpret_cast<const unsigned char*>(base + tc_off_blob(L));
+  p.cbf = reinterpret_cast<const float*>(base + tc_off_cbf(L));
+  p.blob = reinterpret_cast<const unsigned char*>(base + tc_off_blob(D, L));
   p.ids = ids; p.stats = stats; p.sx = 1.0f;
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -815,13 +857,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   const size_t smem = (size_t)TC_MAX_KC * TC_ACHUNK_BYTES + TC_BSTAGES * TC_BSTAGE_BYTES + sizeof(TcSmemMisc);
   static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
   const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-  if (want_trace && stats) {       // caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
-    RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rq_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
-  } else {
-    RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rq_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
-  }
-  RQB_LAUNCH_CHECK();
-  return RQB_OK;
+  const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
+  if (want_trace && stats) return vec_ok ? tc_launch<true, true>(p, grid, smem, st) : tc_launch<true, false>(p, grid, smem, st);
+  return vec_ok ? tc_launch<false, true>(p, grid, smem, st) : tc_launch<false, false>(p, grid, smem, st);
 }
