@@ -104,6 +104,10 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
   }
 }
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map): SASS UBLKCP
+// fire-and-forget L2 prefetch of `bytes` (multiple of 16) from a 16-byte aligned global address
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

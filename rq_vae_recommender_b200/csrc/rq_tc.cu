@@ -268,6 +268,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
+// read-only 128-bit load as a VOLATILE asm: keeps its program position relative to the other volatile asm statements
+// (tcgen05.ld / wait), which is what makes the hand-written software pipelines below survive the compiler's code sinking
+__device__ __forceinline__ float4 ldg_pinned(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 struct TcParams {
   const float* x;
@@ -282,6 +290,9 @@ struct TcParams {
   int64_t* ids;         // [B][L]
   int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
   float sx;             // scale of the fp16 image of x; fixed at 1 (kept in the margin formulas for a future per-call scale)
+  int rot;              // 1: every CTA walks the k chunks from its own starting chunk (blockIdx % nkc), see tc_rot()
+  int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
+  int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
 };
 
 struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
@@ -329,6 +340,28 @@ __device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr));
 }
 
+// one lane of a fully active warp (CUTLASS elect_one_sync idiom).  The producer and MMA warps run their schedules with ALL
+// lanes (warp-uniform control flow) and only issue under this predicate: ptxas then keeps descriptors, addresses and loop
+// state in uniform registers.  Issuing from `if (lane == 0)` divergent code instead cost ~25 instructions (ELECT / PLOP3 /
+// R2UR chains) and ~140 cycles per tcgen05.mma -- more than twice the 64 cycles the tensor core needs to execute it.
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// k-chunk visited at step i: CTAs start at different chunks so that 148 SMs do not all stream the SAME 16 KB codebook block
+// (same L2 lines) at the same moment.  Only the fp32 summation order of the approximate scores changes, which the margin
+// covers; a tile's order depends on the CTA that owns it, which is fixed for a given launch shape.
+__device__ __forceinline__ int tc_rot(int i, int rot0, int nkc) {
+  const int kc = i + rot0;
+  return kc >= nkc ? kc - nkc : kc;
+}
+
 __device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
@@ -346,6 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
   const bool trace = kTrace && p.stats != nullptr;
+  const int rot0 = p.rot ? (int)(blockIdx.x % (unsigned)nkc) : 0;
 
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
@@ -370,19 +404,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     // register budget (per-CTA pool = 512 threads x 128 at launch = 65536): 128x32 + 128x128 + 256x176 = 65536.
     // With the 225 KB shared-memory carve-out there is no L1: a spill is an L2 round trip, so no role may spill in a loop.
     tc_setmaxnreg_dec<32>();
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       uint32_t s = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (kVec && p.prefetch && lane == 0) {
+          // pull the NEXT tile's x rows into L2 now (393 KB per CTA, 58 MB chip-wide: fits the 126 MB L2), so the converter's
+          // loads are L2 hits: with 32 KB of register buffers in flight per SM it cannot cover the HBM latency-bandwidth
+          // product (23 B/clk x ~1500 cycles), it can cover L2's
+          const int nt = tile + gridDim.x;
+          if (nt < p.ntiles) {
+            const int rows = min(TC_BM, p.B - nt * TC_BM);
+            const float* xn = p.x + (int64_t)nt * TC_BM * p.ldx;
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) bulk_prefetch_l2(xn + (int64_t)r * p.ldx, (uint32_t)p.D * 4u);
+          }
+        }
         for (int l = 0; l < L; ++l)
-          for (int kc = 0; kc < nkc; ++kc)
+          for (int i = 0; i < nkc; ++i)
             for (int h = 0; h < 2; ++h, ++s) {      // same order as the MMA issuer: chunk-major, column half inner
+              const int kc = tc_rot(i, rot0, nkc);
               const uint32_t st = s % TC_BSTAGES, u = s / TC_BSTAGES;
               mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);
-              mbar_expect_tx(&ms->b_full[st], TC_BSTAGE_BYTES);
-              bulk_g2s(sB + st * TC_BSTAGE_BYTES, p.blob + (size_t)((l * 2 + h) * nkc + kc) * TC_BSTAGE_BYTES,
-                       TC_BSTAGE_BYTES, &ms->b_full[st]);
+              if (tc_elect_one()) {
+                mbar_expect_tx(&ms->b_full[st], TC_BSTAGE_BYTES);
+                bulk_g2s(sB + st * TC_BSTAGE_BYTES, p.blob + (size_t)((l * 2 + h) * nkc + kc) * TC_BSTAGE_BYTES,
+                         TC_BSTAGE_BYTES, &ms->b_full[st]);
+              }
+              __syncwarp();
             }
-    } else if (warp == 1 && lane == 0) {
+      }
+    } else if (warp == 1) {
       const uint32_t idesc = tc_idesc(128, 128);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t s = 0, g = 0, it = 0;
@@ -400,7 +451,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           // neither epilogue warp of a lane quarter waits for the other's scan to start, and at the last level chunk kc is
           // released after 2 steps instead of 12 + kc, which widens the window for refilling A with the next tile.
           const uint32_t d_base = TC_TMEM_BASE() + buf * 256;
-          for (int kc = 0; kc < nkc; ++kc) {
+          for (int i = 0; i < nkc; ++i) {
+            const int kc = tc_rot(i, rot0, nkc);
             TC_ACC(w_issue, tm);
             if (l == 0) mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
             TC_ACC(w_af, tm);
@@ -411,17 +463,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               TC_ACC(w_bf, tm);
               tc_fence_after();
               const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
+              if (tc_elect_one()) {
 #pragma unroll
-              for (int j = 0; j < TC_KC / 16; ++j)   // K=16 per instruction: +32 B inside the 128 B swizzle row
-                tc_mma_f16(d_base + h * 128, adesc + 2 * j, bdesc + 2 * j, idesc, (kc | j) != 0);
-              tc_commit(&ms->b_empty[st]);
+                for (int j = 0; j < TC_KC / 16; ++j)   // K=16 per instruction: +32 B inside the 128 B swizzle row
+                  tc_mma_f16(d_base + h * 128, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0);
+                tc_commit(&ms->b_empty[st]);
+                if (h == 1 && l == L - 1) tc_commit(&ms->a_empty[kc]);
+                if (h == 1 && i == nkc - 1) {
+                  tc_commit(&ms->t_full[buf][0]);
+                  tc_commit(&ms->t_full[buf][1]);
+                }
+              }
+              __syncwarp();
             }
-            if (l == L - 1) tc_commit(&ms->a_empty[kc]);
           }
-          tc_commit(&ms->t_full[buf][0]);
-          tc_commit(&ms->t_full[buf][1]);
         }
-      if (trace) {
+      if (trace && lane == 0) {
         tc_trace_add(p.stats, 0, w_te); tc_trace_add(p.stats, 1, w_af); tc_trace_add(p.stats, 2, w_bf);
         tc_trace_add(p.stats, 3, clock64() - tm_start); tc_trace_add(p.stats, 12, 1);
       }
@@ -483,11 +540,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
                        "r"(*reinterpret_cast<const uint32_t*>(&h1)) : "memory");
         }
       };
-      const int nh = 2 * nkc;
-      load_half(va, 0);
-      load_half(vb, 1);
+      // chunks are produced in the order the MMA issuer consumes them: step i -> chunk tc_rot(i)
+      load_half(va, 2 * rot0);
+      load_half(vb, 2 * rot0 + 1);
 #pragma unroll 1
-      for (int kc = 0; kc < nkc; ++kc) {
+      for (int i = 0; i < nkc; ++i) {
+        const int kc = tc_rot(i, rot0, nkc);
+        const int kn = tc_rot(i + 1 < nkc ? i + 1 : i, rot0, nkc);    // next chunk (the last step re-loads its own: unused)
         TC_ACC(c_work, tcv);
         mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
         TC_ACC(c_wait, tcv);
@@ -498,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         }
         convert_half(va, 2 * kc);
         TC_ACC(c_cvt, tcv);
-        if (2 * kc + 2 < nh) load_half(va, 2 * kc + 2);
+        if (i + 1 < nkc) load_half(va, 2 * kn);
         if (trace) {
           const float probe = __shfl_sync(0xffffffffu, vb[7].w, 0);
           asm volatile("" ::"f"(probe));
@@ -506,18 +565,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         }
         convert_half(vb, 2 * kc + 1);
         TC_ACC(c_cvt, tcv);
-        if (2 * kc + 3 < nh) load_half(vb, 2 * kc + 3);
-        if (kc == nkc - 1) {
+        if (i + 1 < nkc) load_half(vb, 2 * kn + 1);
+        if (i == nkc - 1) {
           // row statistics for the margin: reduce over the 16 lanes that share a row, publish before the last arrive
           mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {      // the 8 lanes (q8) that share row 4i + rsub
-              sm[i] = fmaxf(sm[i], __shfl_xor_sync(0xffffffffu, sm[i], o));
-              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+            for (int o = 4; o > 0; o >>= 1) {      // the 8 lanes (q8) that share row 4r + rsub
+              sm[r] = fmaxf(sm[r], __shfl_xor_sync(0xffffffffu, sm[r], o));
+              s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
             }
-            if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * i] = (tc_bf16_up(sm[i]) << 16) | tc_bf16_up(s2[i]);
+            if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * r] = (tc_bf16_up(sm[r]) << 16) | tc_bf16_up(s2[r]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -563,10 +622,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float* trow1 = (l >= 2) ? grow(1) : trow0;
         auto load_t = [&](float4 (&ta)[4], float4 (&tb)[4], int col) {      // issue only: nothing here waits for data
 #pragma unroll
-          for (int v = 0; v < 4; ++v) ta[v] = __ldg(reinterpret_cast<const float4*>(trow0 + col) + v);
+          for (int v = 0; v < 4; ++v) ta[v] = ldg_pinned(reinterpret_cast<const float4*>(trow0 + col) + v);
           if (l >= 2) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) tb[v] = __ldg(reinterpret_cast<const float4*>(trow1 + col) + v);
+            for (int v = 0; v < 4; ++v) tb[v] = ldg_pinned(reinterpret_cast<const float4*>(trow1 + col) + v);
           }
         };
         auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {   // called one chunk of compute after load_t
@@ -615,15 +674,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         int i1 = 0, i2 = 0;
         // one 16-column chunk: packed-key triple (7 instructions per score), then one merge into the running top-3
         auto score16 = [&](const uint32_t (&s)[16], const float4 (&t)[4], int col) {
-          float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
+          // The always-true opaque branch makes this ALU block its own basic block.  ptxas otherwise treats the prefetches
+          // issued just above it (Gram rows: an L2 round trip, ~700 cycles; next TMEM columns) as ordinary short loads and
+          // sinks them to the END of the block, a few instructions ahead of their first use -- the software pipeline then
+          // hides nothing (ncu: 660 long-scoreboard samples on the first FFMA after the loads).  Volatile asm and empty-asm
+          // pins fix the order in PTX but not in SASS; a block boundary does.
+          if (p.one) {
+            float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
-            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
-            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
-            tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+            for (int v = 0; v < 4; ++v) {
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+            }
+            tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
           }
-          tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
         };
         fold_t(ta0, tb0, col0);
         // software pipeline, two chunks per trip: the next chunk's Gram rows and TMEM columns are in flight while this one
@@ -635,12 +701,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           tc_ld16_issue(tcol + c + 16, s1);
           score16(s0, ta0, col0 + c);
           fold_t(ta1, tb1, col0 + c + 16);
-          const bool more = c + 32 < 128;                 // warp-uniform
-          if (more) load_t(ta0, tb0, col0 + c + 32);
+          // No `if (last trip)` around the prefetches: a branch here splits the body into basic blocks and ptxas then hoists
+          // the next score16 above the prefetch block (seen in SASS), which exposes the full L2 latency again.  The last trip
+          // harmlessly re-fetches the chunk it just scored.
+          const int cn = min(c + 32, 96);
+          load_t(ta0, tb0, col0 + cn);
           tc_ld_wait();                                   // s1 landed
-          if (more) tc_ld16_issue(tcol + c + 32, s0);
+          tc_ld16_issue(tcol + cn, s0);
           score16(s1, ta1, col0 + c + 16);
-          if (more) fold_t(ta0, tb0, col0 + c + 32);
+          fold_t(ta0, tb0, col0 + cn);
         }
         tc_ld_wait();
 
@@ -847,7 +916,12 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   p.gram = reinterpret_cast<const float*>(base + tc_off_gram(L));
   p.cbf = reinterpret_cast<const float*>(base + tc_off_cbf(L));
   p.blob = reinterpret_cast<const unsigned char*>(base + tc_off_blob(D, L));
-  p.ids = ids; p.stats = stats; p.sx = 1.0f;
+  p.ids = ids; p.stats = stats; p.sx = 1.0f; p.one = 1;
+  // both measured NEGATIVE on B200 (tools/tc_ab.py, same box: rotation +1 %, prefetch +0.5 % time): kept as opt-in knobs so
+  // the measurement can be repeated, off by default
+  static const int opt_rot = []() { const char* e = getenv("RQB200_TC_ROT"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int opt_pf = []() { const char* e = getenv("RQB200_TC_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
+  p.rot = opt_rot; p.prefetch = opt_pf;
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
