@@ -30,6 +30,7 @@
 // Measured limits and the hypotheses tested on the way: DESIGN.md section 5.2, profiles/r1_tc_role_trace.txt.
 #include "common.cuh"
 #include "tc_select.cuh"
+#include <cuda.h>        // CUtensorMap (the CTA-pair variant loads the codebook blocks with tensor-map TMA)
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
@@ -230,6 +231,39 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms, validated standalone by tools/pair_probe.cu.  Issued by the leader CTA (rank 0) only,
+// except alloc / dealloc which warp 1 of BOTH CTAs executes.
+__device__ __forceinline__ void tc_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 (128 rows from each CTA's smem) and N = 256 (128 B rows from each CTA's smem)
+__device__ __forceinline__ void tc_mma_f16_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior tcgen05 ops of this thread -> the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// one box of a 2-D tensor map -> this CTA's shared memory, the bytes counted on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tc_tma2d_pair(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t mbar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -276,8 +310,19 @@ __device__ __forceinline__ float4 ldg_pinned(const float4* p) {
   return v;
 }
 
+// 256-bit flavour (sm_100: LDG.E.256), 32-byte aligned address.  The Gram-row gathers of the scan touch a different 128-byte
+// line in every lane, so the L1TEX data pipe spends one wavefront per lane per instruction whatever the access width: ncu
+// showed that pipe as the busiest unit of the kernel (47 %), with the converter's x loads queueing behind the gathers
+// (timeline: 6.6 K cycles from issue to data).  Twice the bytes per lane per instruction = half the wavefronts.
+__device__ __forceinline__ void ldg256_pinned(const float* p, float4& lo, float4& hi) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+               : "l"(p));
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 struct TcParams {
+  CUtensorMap tmapB;    // pair variant: the fp16 codebook blob as a [blocks*128 rows][64 halves] matrix, box = one 16 KB block
   const float* x;
   int64_t ldx;
   int B, D, L, nkc, ntiles;
@@ -313,6 +358,12 @@ struct TcSmemMisc {
 __device__ __forceinline__ void tc_trace_add(int* stats, int slot, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(stats + 8) + slot, (unsigned long long)v);
 }
+// event timeline of CTA 0 (RQB200_TC_TRACE=1 and stats[4] != 0; the caller passes >= 4096 ints): role r appends
+// (tag << 56 | payload << 48 | clock) records at ((long long*)(stats + 128))[r * 256 ...]; tools/trace_tc.py --timeline prints them
+#define TC_EV_DECL() int ev_n = 0; const bool ev_on = trace && blockIdx.x == 0 && p.stats[4] != 0
+#define TC_EV(role, tag, payload) do { if (ev_on && (threadIdx.x & 31) == 0 && ev_n < 256) { \
+    reinterpret_cast<long long*>(p.stats + 128)[(role) * 256 + ev_n++] = \
+        ((long long)(tag) << 56) | ((long long)((payload) & 0xff) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
 #define TC_T0(var) long long var = trace ? clock64() : 0
 #define TC_ACC(acc, var) do { if (trace) { const long long n__ = clock64(); acc += n__ - var; var = n__; } } while (0)
 
@@ -369,8 +420,13 @@ __device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float
 // kTrace = true compiles the clock64 role accounting in (RQB200_TC_TRACE=1); the production instantiation carries none of it.
 // kVec = false is the slow-path instantiation for x whose rows are not 16-byte aligned (scalar loads); keeping it out of the
 // main instantiation halves the converter's code.
-template <bool kTrace, bool kVec>
-__global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
+// kPair = true is the CTA-pair instantiation (launched as clusters of 2, tcgen05 cta_group::2): the two CTAs of a pair take the
+// two 128-row halves of a 256-row pair-tile; ONE M=256 x N=256 instruction of the leader drives both tensor cores, each CTA
+// streams only ITS half of every codebook block (half the L2 and shared-memory traffic per row, and the same 2 x 16 KB ring
+// now covers twice the tensor time).  Barriers the leader waits on (a_full, b_full, t_empty) collect arrivals from both CTAs;
+// barriers the leader signals (a_empty, b_empty, t_full) are multicast commits.
+template <bool kTrace, bool kVec, bool kPair>
+__global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
   unsigned char* sB = tsm + TC_MAX_KC * TC_ACHUNK_BYTES;           // [TC_BSTAGES][16 KB]
@@ -379,23 +435,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
   const bool trace = kTrace && p.stats != nullptr;
-  const int rot0 = p.rot ? (int)(blockIdx.x % (unsigned)nkc) : 0;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;              // 0 = leader
+  // work units: tiles (one CTA each) or pair-tiles (one cluster each; the CTA takes tile 2*unit + crank, which may lie
+  // past the last tile when the tile count is odd: that CTA still runs the whole protocol on clamped rows and stores nothing)
+  const int u_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int u_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int u_count = kPair ? (p.ntiles + 1) >> 1 : p.ntiles;
+  #define TC_TILE_OF(unit) (kPair ? 2 * (unit) + (int)crank : (unit))
+  const int rot0 = p.rot ? u_first % nkc : 0;     // both CTAs of a pair must walk the chunks in the same order
 
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
-    for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], TC_NCONV_WARPS * 32); mbar_init(&ms->a_empty[i], 1); }
+    // pair: one aggregated arrive per converter / epilogue warp of EACH CTA (remote arrives are per warp, not per thread)
+    for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], kPair ? 2 * TC_NCONV_WARPS : TC_NCONV_WARPS * 32); mbar_init(&ms->a_empty[i], 1); }
     for (int i = 0; i < TC_BSTAGES; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ms->t_full[i][0], 1);
       mbar_init(&ms->t_full[i][1], 1);
-      mbar_init(&ms->t_empty[i], TC_NEPI_WARPS * 32);
+      mbar_init(&ms->t_empty[i], kPair ? 2 * TC_NEPI_WARPS : TC_NEPI_WARPS * 32);
     }
     mbar_init(&ms->rowinfo_free, 128);   // the half-0 epilogue thread of every row
     fence_mbar_init();
   }
-  if (warp == 1) tc_alloc(&ms->tmem_base, 512);
+  if (warp == 1) { if (kPair) tc_alloc2(&ms->tmem_base, 512); else tc_alloc(&ms->tmem_base, 512); }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();     // the peer's barriers are initialised before anything remote touches them
   tc_fence_after();
   #define TC_TMEM_BASE() (*reinterpret_cast<volatile uint32_t*>(&ms->tmem_base))
 
@@ -406,19 +471,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     tc_setmaxnreg_dec<32>();
     if (warp == 0) {
       uint32_t s = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int unit = u_first; unit < u_count; unit += u_step) {
         if (kVec && p.prefetch && lane == 0) {
           // pull the NEXT tile's x rows into L2 now (393 KB per CTA, 58 MB chip-wide: fits the 126 MB L2), so the converter's
           // loads are L2 hits: with 32 KB of register buffers in flight per SM it cannot cover the HBM latency-bandwidth
           // product (23 B/clk x ~1500 cycles), it can cover L2's
-          const int nt = tile + gridDim.x;
-          if (nt < p.ntiles) {
+          const int nt = TC_TILE_OF(unit + u_step);
+          if (unit + u_step < u_count && nt < p.ntiles) {
             const int rows = min(TC_BM, p.B - nt * TC_BM);
             const float* xn = p.x + (int64_t)nt * TC_BM * p.ldx;
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) bulk_prefetch_l2(xn + (int64_t)r * p.ldx, (uint32_t)p.D * 4u);
           }
         }
+        if constexpr (kPair) {
+          // one 16 KB block per chunk step: THIS CTA's 128 codes (column half = crank) of level l, chunk kc; the bytes of both
+          // CTAs are counted on the LEADER's b_full, which is what its MMA warp waits on
+          for (int l = 0; l < L; ++l)
+            for (int i = 0; i < nkc; ++i, ++s) {
+              const int kc = tc_rot(i, rot0, nkc);
+              const uint32_t st = s % TC_BSTAGES, u = s / TC_BSTAGES;
+              mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);      // local: the leader's commits are multicast
+              if (tc_elect_one()) {
+                if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
+                tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, ((l * 2 + (int)crank) * nkc + kc) * 128,
+                              cluster_map(smem_u32(&ms->b_full[st]), 0));
+              }
+              __syncwarp();
+            }
+        } else
         for (int l = 0; l < L; ++l)
           for (int i = 0; i < nkc; ++i)
             for (int h = 0; h < 2; ++h, ++s) {      // same order as the MMA issuer: chunk-major, column half inner
@@ -433,19 +514,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               __syncwarp();
             }
       }
-    } else if (warp == 1) {
-      const uint32_t idesc = tc_idesc(128, 128);
+    } else if (warp == 1 && crank == 0) {
+      const uint32_t idesc = kPair ? tc_idesc(256, 256) : tc_idesc(128, 128);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t s = 0, g = 0, it = 0;
       long long w_te = 0, w_af = 0, w_bf = 0, w_issue = 0;
+      TC_EV_DECL();
       TC_T0(tm);
       const long long tm_start = tm;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it)
+      for (int unit = u_first; unit < u_count; unit += u_step, ++it)
         for (int l = 0; l < L; ++l, ++g) {
           const uint32_t buf = g & 1, u = g >> 1;
           TC_ACC(w_issue, tm);
-          mbar_wait_guarded(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          if (kPair) mbar_wait_guarded_cluster(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          else mbar_wait_guarded(&ms->t_empty[buf], (u & 1) ^ 1, 2);
           TC_ACC(w_te, tm);
+          TC_EV(0, 1, it * 16 + l);
           tc_fence_after();
           // chunk-major order (kc outer, column half inner): both 128-column halves of the score tile complete together, so
           // neither epilogue warp of a lane quarter waits for the other's scan to start, and at the last level chunk kc is
@@ -454,9 +538,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           for (int i = 0; i < nkc; ++i) {
             const int kc = tc_rot(i, rot0, nkc);
             TC_ACC(w_issue, tm);
-            if (l == 0) mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
+            if (l == 0) {
+              if (kPair) mbar_wait_guarded_cluster(&ms->a_full[kc], it & 1, 3);
+              else mbar_wait_guarded(&ms->a_full[kc], it & 1, 3);
+            }
             TC_ACC(w_af, tm);
+            if (l == 0) TC_EV(0, 2, it * 16 + i);
             const uint64_t adesc = tc_smem_desc(a_base + kc * TC_ACHUNK_BYTES);
+            if constexpr (kPair) {
+              const uint32_t st = s % TC_BSTAGES;
+              mbar_wait_guarded_cluster(&ms->b_full[st], (s / TC_BSTAGES) & 1, 4);
+              TC_ACC(w_bf, tm);
+              tc_fence_after();
+              const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
+              if (tc_elect_one()) {
+#pragma unroll
+                for (int j = 0; j < TC_KC / 16; ++j)
+                  tc_mma_f16_2(d_base, adesc + 2 * j, bdesc + 2 * j, idesc, (i | j) != 0);
+                tc_commit2(&ms->b_empty[st]);
+                if (l == L - 1) tc_commit2(&ms->a_empty[kc]);
+                if (i == nkc - 1) {
+                  tc_commit2(&ms->t_full[buf][0]);
+                  tc_commit2(&ms->t_full[buf][1]);
+                }
+              }
+              __syncwarp();
+              ++s;
+            } else
             for (int h = 0; h < 2; ++h, ++s) {
               const uint32_t st = s % TC_BSTAGES;
               mbar_wait_guarded(&ms->b_full[st], (s / TC_BSTAGES) & 1, 4);
@@ -477,6 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
               __syncwarp();
             }
           }
+          TC_EV(0, 3, it * 16 + l);
         }
       if (trace && lane == 0) {
         tc_trace_add(p.stats, 0, w_te); tc_trace_add(p.stats, 1, w_af); tc_trace_add(p.stats, 2, w_bf);
@@ -494,10 +603,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const int rsub = lane >> 3, q8 = lane & 7;
     uint32_t it = 0;
     long long c_wait = 0, c_work = 0, c_ldwait = 0, c_cvt = 0;
+    TC_EV_DECL();
     TC_T0(tcv);
     const long long tcv_start = tcv;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+      const int tile = min(TC_TILE_OF(unit), p.ntiles - 1);   // a pair's second CTA past the last tile converts that tile again (unused)
       // row statistics for the filter margin: max|x| and sum x^2 (sum x^4 <= max|x|^2 * sum x^2 is used downstream; max|x|
       // doubles as the fp16 overflow test, NaN inputs surface through sum x^2).  ~half the ALU of tracking sum x^4 and
       // testing every converted half for inf.
@@ -550,6 +661,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         TC_ACC(c_work, tcv);
         mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
         TC_ACC(c_wait, tcv);
+        if (cw == 0) TC_EV(1, 1, it * 16 + i);
         if (trace) {   // split "waiting for the loads to land" from "convert + store": shfl needs the last-issued value
           const float probe = __shfl_sync(0xffffffffu, va[7].w, 0);
           asm volatile("" ::"f"(probe));
@@ -580,7 +692,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&ms->a_full[kc]);
+        if constexpr (kPair) {               // one arrive per warp on the LEADER's barrier (remote for the peer CTA)
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->a_full[kc]), 0));
+        } else {
+          mbar_arrive(&ms->a_full[kc]);
+        }
+        if (cw == 0) TC_EV(1, 2, it * 16 + i);
       }
     }
     if (trace && cw == 0 && lane == 0) {
@@ -601,10 +719,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
     const int lane4 = lane * 4;
     uint32_t g = 0, it = 0;
     long long e_tf = 0, e_scan = 0, e_pair = 0, e_rr = 0, e_idw = 0, e_merge = 0, e_many = 0;
+    TC_EV_DECL();
+    const int ev_role = 2 + half;      // lane quarter 0 only
     TC_T0(te);
     const long long te_start = te;
+    // accumulator buffer released: per thread locally, or one arrive per warp on the LEADER's barrier in the pair variant
+    auto release_tmem = [&](uint32_t buf) {
+      tc_fence_before();
+      if constexpr (kPair) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->t_empty[buf]), 0));
+      } else {
+        mbar_arrive(&ms->t_empty[buf]);
+      }
+    };
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+      const int tile = TC_TILE_OF(unit);
       const int row = tile * TC_BM + r_local;
       const bool valid = row < p.B;    // rows past B run the same code on zero scores (no divergent copies); nothing of theirs is stored
       uint64_t idpack = 0;          // 8 bits per level
@@ -622,10 +753,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         const float* trow1 = (l >= 2) ? grow(1) : trow0;
         auto load_t = [&](float4 (&ta)[4], float4 (&tb)[4], int col) {      // issue only: nothing here waits for data
 #pragma unroll
-          for (int v = 0; v < 4; ++v) ta[v] = ldg_pinned(reinterpret_cast<const float4*>(trow0 + col) + v);
+          for (int v = 0; v < 4; v += 2) ldg256_pinned(trow0 + col + 4 * v, ta[v], ta[v + 1]);
           if (l >= 2) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) tb[v] = ldg_pinned(reinterpret_cast<const float4*>(trow1 + col) + v);
+            for (int v = 0; v < 4; v += 2) ldg256_pinned(trow1 + col + 4 * v, tb[v], tb[v + 1]);
           }
         };
         auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {   // called one chunk of compute after load_t
@@ -634,11 +765,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
             for (int v = 0; v < 4; ++v) { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
 #pragma unroll 1
             for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
-              const float4* gj = reinterpret_cast<const float4*>(grow(j) + col);
+              const float* gj = grow(j) + col;
 #pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const float4 t = __ldg(gj + v);
-                ta[v].x += t.x; ta[v].y += t.y; ta[v].z += t.z; ta[v].w += t.w;
+              for (int v = 0; v < 4; v += 2) {
+                float4 t0, t1;
+                ldg256_pinned(gj + 4 * v, t0, t1);
+                ta[v].x += t0.x; ta[v].y += t0.y; ta[v].z += t0.z; ta[v].w += t0.w;
+                ta[v + 1].x += t1.x; ta[v + 1].y += t1.y; ta[v + 1].z += t1.z; ta[v + 1].w += t1.w;
               }
             }
           }
@@ -649,6 +782,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         TC_ACC(e_rr, te);
         mbar_wait_guarded(&ms->t_full[buf][half], u & 1, 7);
         TC_ACC(e_tf, te);
+        if (quarter == 0) TC_EV(ev_role, 1, it * 16 + l);
         tc_fence_after();
         const uint32_t tcol = TC_TMEM_BASE() + lane_addr + buf * 256 + col0;
         uint32_t s0[16], s1[16];
@@ -714,15 +848,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         tc_ld_wait();
 
         TC_ACC(e_scan, te);
+        if (quarter == 0) TC_EV(ev_role, 2, it * 16 + l);
         if (half == 1) {
           // ---- hand the top-3 of columns [128,256) to the half-0 warp of this lane quarter, then wait for the final id
           TcExch e; e.m1 = m1; e.m2 = m2; e.m3 = m3; e.idx = (uint32_t)i1 | ((uint32_t)i2 << 8);
           ms->exch[r_local] = e;
-          tc_fence_before();
-          mbar_arrive(&ms->t_empty[buf]);
+          release_tmem(buf);
           tc_pair_arrive(bar_x);
           tc_pair_sync(bar_i);
           TC_ACC(e_idw, te);
+          if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
           idpack |= (uint64_t)(ms->exch[r_local].idx & 0xff) << (8 * l);
           continue;
         }
@@ -744,6 +879,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         // so it is only touched on that rare path: every word is written inside `if (mn)` before the re-rank reads it.
         uint32_t mask[8];
         TC_ACC(e_merge, te);
+        if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
         if (mn) {
           // second pass over all 256 raw scores (warp-uniform branch): exact candidate bitmask for the `many` rows
           const uint32_t tall = TC_TMEM_BASE() + lane_addr + buf * 256;
@@ -771,8 +907,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
           }
         }
         TC_ACC(e_many, te);
-        tc_fence_before();
-        mbar_arrive(&ms->t_empty[buf]);     // accumulator buffer may be overwritten by level l+2
+        release_tmem(buf);
+        if (quarter == 0) TC_EV(ev_role, 4, it * 16 + l);                  // accumulator buffer may be overwritten by level l+2
 
         int my_id = i1;
         // ---- warp-cooperative exact re-rank of the flagged rows (same arithmetic as rq_simt.cu: sequential fp32 residual,
@@ -868,6 +1004,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
         idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
         ms->exch[r_local].idx = (uint32_t)my_id;     // publish the final id of this level to the half-1 warp
         tc_pair_arrive(bar_i);
+        if (quarter == 0) TC_EV(ev_role, 5, it * 16 + l);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
       }
     }
@@ -882,17 +1019,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(TcParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();     // neither CTA may exit (or free TMEM) while the other can still reach into it
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(TC_TMEM_BASE(), 512);
+    if (kPair) tc_dealloc2(TC_TMEM_BASE(), 512); else tc_dealloc(TC_TMEM_BASE(), 512);
   }
 }
 
-template <bool kTrace, bool kVec>
+template <bool kTrace, bool kVec, bool kPair>
 static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-  RQB_CUDA(cudaFuncSetAttribute(rq_tc_kernel<kTrace, kVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rq_tc_kernel<kTrace, kVec><<<grid, TC_THREADS, smem, st>>>(p);
+  auto kern = rq_tc_kernel<kTrace, kVec, kPair>;
+  RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (kPair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RQB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, TC_THREADS, smem, st>>>(p);
+  }
   RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}
+
+template <bool kPair>
+static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, bool vec_ok) {
+  if (trace) return vec_ok ? tc_launch<true, true, kPair>(p, grid, smem, st) : tc_launch<true, false, kPair>(p, grid, smem, st);
+  return vec_ok ? tc_launch<false, true, kPair>(p, grid, smem, st) : tc_launch<false, false, kPair>(p, grid, smem, st);
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tc_encode_blob_map(CUtensorMap* tm, const void* blob, int nblocks) {
+  static TcEncodeFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RQB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess) {
+      rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return RQB_ERR_UNSUPPORTED;
+    }
+    fn = reinterpret_cast<TcEncodeFn>(f);
+  }
+  // the blob is a sequence of pre-swizzled 16 KB images = 128 rows of 128 bytes each: a [nblocks*128][64] fp16 matrix whose
+  // box {64, 128} is exactly one image; no swizzle here, the bytes are already in the tcgen05 shared-memory order
+  const cuuint64_t gdim[2] = {64, (cuuint64_t)nblocks * 128};
+  const cuuint64_t gstr[1] = {128};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RQB_ERR_CUDA;
+  }
   return RQB_OK;
 }
 
@@ -930,9 +1121,17 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   }
   const size_t smem = (size_t)TC_MAX_KC * TC_ACHUNK_BYTES + TC_BSTAGES * TC_BSTAGE_BYTES + sizeof(TcSmemMisc);
   static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
-  const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
   const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
-  if (want_trace && stats) return vec_ok ? tc_launch<true, true>(p, grid, smem, st) : tc_launch<true, false>(p, grid, smem, st);
-  return vec_ok ? tc_launch<false, true>(p, grid, smem, st) : tc_launch<false, false>(p, grid, smem, st);
+  const bool trace = want_trace && stats;       // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
+  // CTA-pair variant (cta_group::2): opt-in while it is being brought up
+  static const int opt_pair = []() { const char* e = getenv("RQB200_TC_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (opt_pair && p.ntiles >= 2 && sm_count >= 2) {
+    int rc = tc_encode_blob_map(&p.tmapB, p.blob, L * 2 * p.nkc);
+    if (rc) return rc;
+    const int npairs = (p.ntiles + 1) / 2;
+    const int nclusters = npairs < sm_count / 2 ? npairs : sm_count / 2;
+    return tc_dispatch<true>(p, 2 * nclusters, smem, st, trace, vec_ok);
+  }
+  const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
+  return tc_dispatch<false>(p, grid, smem, st, trace, vec_ok);
 }
