@@ -122,3 +122,36 @@ def test_tc_max_levels(ops):
     n_tie = assert_ids_match(ids, O.rq_tokenize(x[:600], cbs), x[:600], cbs, "tc L=8")
     assert n_tie <= 2
     assert not ops.tc_supported(64, 256, 9)
+
+
+@pytest.mark.gpu
+def test_cta_pair_variant_returns_the_same_ids(tmp_path):
+    """The opt-in CTA-pair instantiation (RQB200_TC_PAIR=1: clusters of 2, tcgen05 cta_group::2, tensor-map TMA signalling the
+    leader's mbarrier) must return exactly the ids of the default single-CTA kernel, including an odd tile count (the pair's
+    second CTA then runs past the last tile) and a partial last tile.  The switch is read once per process, hence the
+    subprocess, which writes its ids to disk."""
+    import os, subprocess, sys
+    from rq_vae_recommender_b200 import ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shapes = [(129, 768, 3), (513, 256, 4), (1000, 768, 3)]
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests', 'golden')!r})\n"
+        "import inputs as I\n"
+        "from rq_vae_recommender_b200 import ops\n"
+        f"for (B, D, L) in {shapes!r}:\n"
+        "    x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D); x = x[:B]\n"
+        "    ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs])\n"
+        f"    np.save({str(tmp_path)!r} + f'/pair_{{B}}_{{D}}_{{L}}.npy', ids.cpu().numpy())\n"
+        "print('PAIR DONE')\n"
+    )
+    env = dict(os.environ, RQB200_TC_PAIR="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "PAIR DONE" in res.stdout, res.stdout + res.stderr
+    assert os.environ.get("RQB200_TC_PAIR", "0") != "1", "run this test with the default (single-CTA) kernel in the parent process"
+    for (B, D, L) in shapes:
+        x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D)
+        x = x[:B]
+        ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs]).cpu().numpy()
+        pair = np.load(tmp_path / f"pair_{B}_{D}_{L}.npy")
+        assert np.array_equal(ids, pair), (B, D, L, int((ids != pair).any(axis=1).sum()))
