@@ -28,57 +28,12 @@
 // With the 225 KB shared-memory carve-out there is no L1, so a register spill is an L2 round trip: the hot loops are kept
 // spill-free (checked in SASS) and the role budgets sum to the CTA's launch allocation (setmaxnreg draws from it).
 // Measured limits and the hypotheses tested on the way: DESIGN.md section 5.2, profiles/r1_tc_role_trace.txt.
-#include "common.cuh"
-#include "tc_select.cuh"
-#include <cuda.h>        // CUtensorMap (the CTA-pair variant loads the codebook blocks with tensor-map TMA)
-#include <cuda_fp16.h>
-#include <cmath>
-#include <cstdlib>
+#include "tc_common.cuh"
 
 extern "C" int rqb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int64_t lda,
                             const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int relu,
                             const float* mask, int64_t ldmask, void* stream);
 
-#define TC_K 256          // codes per level (fixed)
-#define TC_BM 128         // rows per tile
-#define TC_KC 64          // fp16 elements per 128-byte swizzle row
-#define TC_MAX_D 768
-#define TC_MAX_KC (TC_MAX_D / TC_KC)
-#define TC_BSTAGES 2
-#define TC_BSTAGE_BYTES (128 * TC_KC * 2)   // 128 codes x 64 k x fp16 = 16 KB
-#define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
-#define TC_NCONV_WARPS 4
-#define TC_NEPI_WARPS 8
-#define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 4 converters | 8 epilogue (2 per TMEM lane quarter) = 512 threads
-// Margin multiplier on the statistical fp16 rounding bound sigma' (DESIGN.md "filter error bound").  Validated with the
-// sum-x^4 statistic at z = 6 (worst observed error 2.3 sigma' over 12.6 M pairs).  The cheaper statistic now in use,
-// sum x^4 <= max|x|^2 sum x^2, makes sigma' ~1.38x larger on gaussian-like rows, so z = 6 / 1.38 keeps the SAME
-// effective margin that was validated instead of an accidentally wider one (which only adds re-rank work).
-#define TC_Z 4.5f
-
-struct TcLevelConst {
-  float sc;      // power-of-two scale applied to the codebook before fp16 conversion
-  float c4max;   // max_k sqrt(sum_d c^4)
-  float c1max;   // max_k sum_d |c|
-  float c2max;   // max_k ||c||_2
-  float gerr;    // bound on the fp32 rounding of the Gram corrections of this level
-  float pad[3];
-};
-
-struct TcHeader {
-  TcLevelConst lv[RQB_MAX_LEVELS];
-  unsigned int amax_bits[RQB_MAX_LEVELS];  // scratch of prepare
-  unsigned int c4_bits[RQB_MAX_LEVELS];
-  unsigned int c1_bits[RQB_MAX_LEVELS];
-  unsigned int c2_bits[RQB_MAX_LEVELS];
-};
-
-static size_t tc_off_cc(int L) { return rqb_round_up(sizeof(TcHeader), 256); }
-static size_t tc_off_hcc(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
-static size_t tc_off_gram(int L) { return tc_off_hcc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
-static size_t tc_off_cbptr(int L) { return tc_off_gram(L) + (size_t)(L * (L - 1) / 2) * TC_K * TC_K * 4; }
-static size_t tc_off_cbf(int L) { return rqb_round_up(tc_off_cbptr(L) + RQB_MAX_LEVELS * 8, 256); }   // fp32 copy [L][256][D]
-static size_t tc_off_blob(int D, int L) { return rqb_round_up(tc_off_cbf(L) + (size_t)L * TC_K * D * 4, 1024); }
 
 extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) {
   return (K == TC_K && D >= TC_KC && D <= TC_MAX_D && D % TC_KC == 0 && L >= 1 && L <= RQB_MAX_LEVELS) ? 1 : 0;
@@ -209,138 +164,6 @@ extern "C" int rqb200_tokenize_tc_prepare(const float* const* codebooks, int D, 
   return RQB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ tcgen05 wrappers
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// ---- CTA-pair (cta_group::2) forms, validated standalone by tools/pair_probe.cu.  Issued by the leader CTA (rank 0) only,
-// except alloc / dealloc which warp 1 of BOTH CTAs executes.
-__device__ __forceinline__ void tc_alloc2(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A * B^T with M = 256 (128 rows from each CTA's smem) and N = 256 (128 B rows from each CTA's smem)
-__device__ __forceinline__ void tc_mma_f16_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// completion of all prior tcgen05 ops of this thread -> the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// one box of a 2-D tensor map -> this CTA's shared memory, the bytes counted on an mbarrier that may live in the peer CTA
-__device__ __forceinline__ void tc_tma2d_pair(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t mbar_cluster_addr) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 consecutive fp32 columns of this thread's TMEM lane (row); asynchronous until tc_ld_wait()
-__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B: 8 rows x 128 B)
-// | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=B=f16 (0), both K-major, N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
-// read-only 128-bit load as a VOLATILE asm: keeps its program position relative to the other volatile asm statements
-// (tcgen05.ld / wait), which is what makes the hand-written software pipelines below survive the compiler's code sinking
-__device__ __forceinline__ float4 ldg_pinned(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-
-// 256-bit flavour (sm_100: LDG.E.256), 32-byte aligned address.  The Gram-row gathers of the scan touch a different 128-byte
-// line in every lane, so the L1TEX data pipe spends one wavefront per lane per instruction whatever the access width: ncu
-// showed that pipe as the busiest unit of the kernel (47 %), with the converter's x loads queueing behind the gathers
-// (timeline: 6.6 K cycles from issue to data).  Twice the bytes per lane per instruction = half the wavefronts.
-__device__ __forceinline__ void ldg256_pinned(const float* p, float4& lo, float4& hi) {
-  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-               : "l"(p));
-}
-
-// ------------------------------------------------------------------------------------------------ main kernel
-struct TcParams {
-  CUtensorMap tmapB;    // pair variant: the fp16 codebook blob as a [blocks*128 rows][64 halves] matrix, box = one 16 KB block
-  const float* x;
-  int64_t ldx;
-  int B, D, L, nkc, ntiles;
-  const TcHeader* hdr;
-  const float* cc;      // [L][256]
-  const float* hcc;     // [L][256]  cc / 2
-  const float* gram;    // [L(L-1)/2][256][256]
-  const float* cbf;     // [L][256][D] fp32 codebook copy (exact re-rank), rows 256-byte aligned
-  const unsigned char* blob;
-  int64_t* ids;         // [B][L]
-  int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
-  float sx;             // scale of the fp16 image of x; fixed at 1 (kept in the margin formulas for a future per-call scale)
-  int rot;              // 1: every CTA walks the k chunks from its own starting chunk (blockIdx % nkc), see tc_rot()
-  int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
-  int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
-};
-
-struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
 
 struct TcSmemMisc {
   uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
@@ -354,68 +177,6 @@ struct TcSmemMisc {
   TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
 };
 
-// optional cycle accounting: when stats[3] != 0 the caller passed >= 64 ints; 64-bit accumulators start at stats[8]
-__device__ __forceinline__ void tc_trace_add(int* stats, int slot, long long v) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(stats + 8) + slot, (unsigned long long)v);
-}
-// event timeline of CTA 0 (RQB200_TC_TRACE=1 and stats[4] != 0; the caller passes >= 4096 ints): role r appends
-// (tag << 56 | payload << 48 | clock) records at ((long long*)(stats + 128))[r * 256 ...]; tools/trace_tc.py --timeline prints them
-#define TC_EV_DECL() int ev_n = 0; const bool ev_on = trace && blockIdx.x == 0 && p.stats[4] != 0
-#define TC_EV(role, tag, payload) do { if (ev_on && (threadIdx.x & 31) == 0 && ev_n < 256) { \
-    reinterpret_cast<long long*>(p.stats + 128)[(role) * 256 + ev_n++] = \
-        ((long long)(tag) << 56) | ((long long)((payload) & 0xff) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
-#define TC_T0(var) long long var = trace ? clock64() : 0
-#define TC_ACC(acc, var) do { if (trace) { const long long n__ = clock64(); acc += n__ - var; var = n__; } } while (0)
-
-template <int N> __device__ __forceinline__ void tc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void tc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void tc_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void tc_pair_arrive(int id) {
-  __threadfence_block();
-  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
-}
-
-__device__ __forceinline__ uint32_t tc_bf16_up(float v) {   // bf16 bits of the smallest bf16 >= v (v >= 0, inf/nan kept)
-  uint32_t b = __float_as_uint(v);
-  if ((b & 0x7f800000u) != 0x7f800000u && (b & 0xffffu)) b += 0x10000u;
-  return b >> 16;
-}
-
-// 16 consecutive fp32 columns of this thread's TMEM lane (row); asynchronous until tc_ld_wait()
-__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-
-// one lane of a fully active warp (CUTLASS elect_one_sync idiom).  The producer and MMA warps run their schedules with ALL
-// lanes (warp-uniform control flow) and only issue under this predicate: ptxas then keeps descriptors, addresses and loop
-// state in uniform registers.  Issuing from `if (lane == 0)` divergent code instead cost ~25 instructions (ELECT / PLOP3 /
-// R2UR chains) and ~140 cycles per tcgen05.mma -- more than twice the 64 cycles the tensor core needs to execute it.
-__device__ __forceinline__ bool tc_elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// k-chunk visited at step i: CTAs start at different chunks so that 148 SMs do not all stream the SAME 16 KB codebook block
-// (same L2 lines) at the same moment.  Only the fp32 summation order of the approximate scores changes, which the margin
-// covers; a tile's order depends on the CTA that owns it, which is fixed for a given launch shape.
-__device__ __forceinline__ int tc_rot(int i, int rot0, int nkc) {
-  const int kc = i + rot0;
-  return kc >= nkc ? kc - nkc : kc;
-}
-
-__device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float acc) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
-}
 
 // kTrace = true compiles the clock64 role accounting in (RQB200_TC_TRACE=1); the production instantiation carries none of it.
 // kVec = false is the slow-path instantiation for x whose rows are not 16-byte aligned (scalar loads); keeping it out of the
