@@ -816,38 +816,6 @@ static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st
   return vec_ok ? tc_launch<false, true, kPair>(p, grid, smem, st) : tc_launch<false, false, kPair>(p, grid, smem, st);
 }
 
-// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
-typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int tc_encode_blob_map(CUtensorMap* tm, const void* blob, int nblocks) {
-  static TcEncodeFn fn = nullptr;
-  if (!fn) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    RQB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
-    if (!f || q != cudaDriverEntryPointSuccess) {
-      rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled is not available from this driver");
-      return RQB_ERR_UNSUPPORTED;
-    }
-    fn = reinterpret_cast<TcEncodeFn>(f);
-  }
-  // the blob is a sequence of pre-swizzled 16 KB images = 128 rows of 128 bytes each: a [nblocks*128][64] fp16 matrix whose
-  // box {64, 128} is exactly one image; no swizzle here, the bytes are already in the tcgen05 shared-memory order
-  const cuuint64_t gdim[2] = {64, (cuuint64_t)nblocks * 128};
-  const cuuint64_t gstr[1] = {128};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return RQB_ERR_CUDA;
-  }
-  return RQB_OK;
-}
-
 extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const void* state, int D, int K, int L,
                                       int64_t* ids, int* stats, void* stream) {
   if (!rqb200_tokenize_tc_supported(D, K, L)) {
@@ -884,6 +852,9 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
   const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool trace = want_trace && stats;       // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
+  // 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M = 128 CTA-pair MMAs, x staged by TMA): opt-in, not yet run on hardware
+  static const int opt_64 = []() { const char* e = getenv("RQB200_TC_64"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (opt_64 && vec_ok && sm_count >= 2) return tc64_run(p, sm_count, trace, st);
   // CTA-pair variant (cta_group::2): opt-in while it is being brought up
   static const int opt_pair = []() { const char* e = getenv("RQB200_TC_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
   if (opt_pair && p.ntiles >= 2 && sm_count >= 2) {

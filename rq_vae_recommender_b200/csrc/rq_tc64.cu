@@ -1,0 +1,546 @@
+// Tensor-core tokeniser, 64 rows per CTA: M = 128 CTA-pair MMAs, x staged through shared memory by TMA.
+//
+// Same result contract, same prepared state and same filter / re-rank arithmetic as rq_tc_kernel (csrc/rq_tc.cu, whose header
+// states the algorithm; reference: modules/quantize.py:113-128,159-161 x L + modules/rqvae.py:125-132).  What changes is
+// where the bytes live, because the 128-row kernel is out of shared memory (A resident = 192 KB of 227 KB):
+//   * its x path (LDG -> registers -> fp16 -> smem) can keep only ~32 KB in flight per SM and shares the L1TEX/LSU path
+//     with the epilogue's gathers: measured 5-6 B/clk/SM against an HBM share of 23 B/clk/SM, pacing level 0 of every tile;
+//   * its codebook ring is 2 x 16 KB, so levels 1-2 run at the L2 latency, not at the tensor rate.
+// Here a cluster of two CTAs owns a 128-row pair-tile, 64 rows each:
+//   A (fp16 image of x)   12 x 8 KB = 96 KB resident per CTA (K-major SWIZZLE_128B, 64 rows)
+//   x staging             TC64_NX x 16 KB: 64 rows x 64 fp32 boxes of a 2-D tensor map over x (TMA, no LSU, zero-filled past B)
+//   B ring                TC64_NB x 16 KB: this CTA's 128 codes of a (level, k chunk) block (tensor-map TMA, cta_group::2)
+//   MMA                   tcgen05.mma.cta_group::2.kind::f16, M = 128 (64 rows from each CTA) x N = 256 x K = 16, issued by the
+//                         leader; the guide's pacing law gives it the full per-SM rate (max(M,128) N / (256 x 2) = 64 cycles)
+//   accumulators          "2x2" TMEM layout (cute tmem_frg_2sm, M_MMA_SM = 64): row m of this CTA sits in lane m for codes
+//                         [0,128) and in lane 64 + m for codes [128,256), so a level needs 128 columns -> FOUR accumulator
+//                         buffers (the 128-row kernel has two), and every one of the 128 lanes is used
+//   epilogue              8 warps: warp (quarter, sub) scans TMEM lanes [32 quarter, +32), columns [64 sub, +64) = rows
+//                         32 (quarter & 1) + lane, codes 128 (quarter >> 1) + 64 sub + [0,64); the four partial top-3 of a row
+//                         meet in shared memory, the (quarter < 2, sub 0) warp owns merge / re-rank / ids
+// STATUS: written without GPU access at the end of round 1 (the round's GPU budget was spent).  It compiles for sm_100a and
+// its index arithmetic is unit-tested on the host (tests/test_tc64_layout.py), but it has NOT run on hardware: it is opt-in
+// (RQB200_TC_64=1) and bring-up starts with tools/pair64_probe.cu (TMEM layout, TMA box, M=128 pair throughput).
+#include "tc_common.cuh"
+#include "tc64_layout.cuh"
+
+#define TC64_BM 64                                  // rows per CTA
+#define TC64_ACHUNK_BYTES (TC64_BM * TC_KC * 2)     // 8 KB
+#define TC64_XSTAGE_BYTES (TC64_BM * TC_KC * 4)     // 16 KB: 64 rows x 64 fp32
+#ifndef TC64_NB
+#define TC64_NB 4
+#endif
+#ifndef TC64_NX
+#define TC64_NX 3
+#endif
+#define TC64_NBUF 4                                 // accumulator buffers of 128 TMEM columns
+
+struct Tc64Misc {
+  uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
+  uint64_t b_full[TC64_NB], b_empty[TC64_NB];
+  uint64_t x_full[TC64_NX], x_empty[TC64_NX];
+  uint64_t t_full[TC64_NBUF], t_empty[TC64_NBUF];
+  uint64_t rowinfo_free;
+  uint32_t tmem_base;
+  uint32_t many_word[2];          // per row group: ballot of the rows with >= 3 candidates at the level being merged
+  uint32_t pad;
+  uint32_t rowinfo[TC64_BM];      // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
+  float thr[TC64_BM];             // candidate threshold of the level being merged (owner -> partner warps, `many` rows)
+  uint32_t idpub[TC64_BM];        // final id of the level (owner -> partner warps)
+  TcExch exch[3][TC64_BM];        // partner slot -> row: top-3 of that warp's 64 columns
+  uint32_t mask[TC64_BM][8];      // candidate bitmask of the `many` rows (each warp writes the 2 words of its 64 columns)
+};
+
+__device__ __forceinline__ void tc64_tma2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// named barriers of one row group (4 warps = 128 threads)
+__device__ __forceinline__ void tc64_grp_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tc64_grp_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 128;" ::"r"(id) : "memory");
+}
+
+template <bool kTrace>
+__global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* sA = tsm;                                             // [TC_MAX_KC][8 KB]
+  unsigned char* sB = sA + TC_MAX_KC * TC64_ACHUNK_BYTES;              // [TC64_NB][16 KB]
+  unsigned char* sX = sB + TC64_NB * TC_BSTAGE_BYTES;                  // [TC64_NX][16 KB]
+  Tc64Misc* ms = reinterpret_cast<Tc64Misc*>(sX + TC64_NX * TC64_XSTAGE_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkc = p.nkc, L = p.L;
+  const bool trace = kTrace && p.stats != nullptr;
+  const uint32_t crank = cluster_ctarank();                           // 0 = leader
+  // work unit = pair-tile of 128 rows (one cluster); this CTA takes the 64-row tile 2 * unit + crank
+  const int u_first = (int)(blockIdx.x >> 1), u_step = (int)(gridDim.x >> 1);
+  const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
+  const int u_count = (ntiles64 + 1) >> 1;
+
+  if (tid == 0) {
+    if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
+    for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], 2 * TC_NCONV_WARPS); mbar_init(&ms->a_empty[i], 1); }
+    for (int i = 0; i < TC64_NB; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
+    for (int i = 0; i < TC64_NX; ++i) { mbar_init(&ms->x_full[i], 1); mbar_init(&ms->x_empty[i], TC_NCONV_WARPS); }
+    for (int i = 0; i < TC64_NBUF; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS); }
+    mbar_init(&ms->rowinfo_free, TC64_BM);       // the owner thread of every row
+    fence_mbar_init();
+  }
+  if (warp == 1) tc_alloc2(&ms->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                // the peer's barriers are initialised before anything remote touches them
+  tc_fence_after();
+  #define TC64_TMEM_BASE() (*reinterpret_cast<volatile uint32_t*>(&ms->tmem_base))
+
+  if (warp < 4) {
+    // ============================================================== warpgroup 0: B producer, MMA issuer, x producer
+    tc_setmaxnreg_dec<32>();
+    if (warp == 0) {
+      // this CTA's 128 codes (column half = crank) of every (level, k chunk) block; the bytes of both CTAs are counted on
+      // the LEADER's b_full, which is what its MMA warp waits on
+      uint32_t s = 0;
+      for (int unit = u_first; unit < u_count; unit += u_step)
+        for (int l = 0; l < L; ++l)
+          for (int kc = 0; kc < nkc; ++kc, ++s) {
+            const uint32_t st = s % TC64_NB, u = s / TC64_NB;
+            mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);      // local: the leader's commits are multicast
+            if (tc_elect_one()) {
+              if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
+              tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, ((l * 2 + (int)crank) * nkc + kc) * 128,
+                            cluster_map(smem_u32(&ms->b_full[st]), 0));
+            }
+            __syncwarp();
+          }
+    } else if (warp == 1 && crank == 0) {
+      const uint32_t idesc = tc_idesc(128, 256);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      uint32_t s = 0, g = 0, it = 0;
+      TC_EV_DECL();
+      for (int unit = u_first; unit < u_count; unit += u_step, ++it)
+        for (int l = 0; l < L; ++l, ++g) {
+          const uint32_t buf = g % TC64_NBUF, u = g / TC64_NBUF;
+          mbar_wait_guarded_cluster(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          TC_EV(0, 1, it * 16 + l);
+          tc_fence_after();
+          const uint32_t d_tmem = TC64_TMEM_BASE() + buf * 128;
+          for (int kc = 0; kc < nkc; ++kc, ++s) {
+            if (l == 0) {
+              mbar_wait_guarded_cluster(&ms->a_full[kc], it & 1, 3);
+              TC_EV(0, 2, it * 16 + kc);
+            }
+            const uint32_t st = s % TC64_NB;
+            mbar_wait_guarded_cluster(&ms->b_full[st], (s / TC64_NB) & 1, 4);
+            tc_fence_after();
+            const uint64_t adesc = tc_smem_desc(a_base + kc * TC64_ACHUNK_BYTES);
+            const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
+            if (tc_elect_one()) {
+#pragma unroll
+              for (int j = 0; j < TC_KC / 16; ++j)   // K=16 per instruction: +32 B inside the 128 B swizzle row
+                tc_mma_f16_2(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kc | j) != 0);
+              tc_commit2(&ms->b_empty[st]);
+              if (l == L - 1) tc_commit2(&ms->a_empty[kc]);
+              if (kc == nkc - 1) tc_commit2(&ms->t_full[buf]);
+            }
+            __syncwarp();
+          }
+          TC_EV(0, 3, it * 16 + l);
+        }
+    } else if (warp == 2) {
+      // x producer: one 64-row x 64-float box per k chunk.  Rows past B read as zero (tensor-map bounds); a pair's second
+      // CTA past the last 64-row tile loads the last tile again (its scores are never stored).
+      uint32_t s = 0;
+      for (int unit = u_first; unit < u_count; unit += u_step) {
+        const int tile = min(2 * unit + (int)crank, ntiles64 - 1);
+        for (int kc = 0; kc < nkc; ++kc, ++s) {
+          const uint32_t st = s % TC64_NX, u = s / TC64_NX;
+          mbar_wait_guarded(&ms->x_empty[st], (u & 1) ^ 1, 8);
+          if (tc_elect_one()) {
+            mbar_expect_tx(&ms->x_full[st], TC64_XSTAGE_BYTES);
+            tc64_tma2d(sX + st * TC64_XSTAGE_BYTES, &p.tmapX, kc * TC_KC, tile * TC64_BM, &ms->x_full[st]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 4 + TC_NCONV_WARPS) {
+    // ============================================================== warpgroup 1: fp32 staging -> fp16 swizzled A chunks
+    // Warp cw owns rows [16cw, 16cw+16) of every chunk; step j covers rows 16cw + 2j + (lane >> 4), float4 column lane & 15:
+    // a warp reads 512 contiguous staging bytes (LDS.128, conflict-free) and writes two 128-byte A rows (STS.64).
+    const int cw = warp - 4;
+    const int hi = lane >> 4, q = lane & 15;
+    uint32_t it = 0, s = 0;
+    TC_EV_DECL();
+#pragma unroll 1
+    for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+      float sm[8], s2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm[j] = 0.f; s2[j] = 0.f; }
+#pragma unroll 1
+      for (int kc = 0; kc < nkc; ++kc, ++s) {
+        const uint32_t st = s % TC64_NX;
+        mbar_wait_guarded(&ms->x_full[st], (s / TC64_NX) & 1, 9);
+        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);     // the last level of the previous tile released this chunk
+        if (cw == 0) TC_EV(1, 1, it * 16 + kc);
+        const unsigned char* xs = sX + st * TC64_XSTAGE_BYTES;
+        const uint32_t a_chunk = smem_u32(sA) + kc * TC64_ACHUNK_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = 16 * cw + 2 * j + hi;
+          const float4 a = *reinterpret_cast<const float4*>(xs + tc64_stage_offset(r, q));
+          s2[j] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, s2[j]))));
+          sm[j] = fmaxf(fmaxf(sm[j], fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+          const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_chunk + tc64_a_offset(r, q)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)) : "memory");
+        }
+        if (kc == nkc - 1) {
+          // row statistics for the margin: reduce over the 16 lanes that share a row, publish before the last arrive
+          mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              sm[j] = fmaxf(sm[j], __shfl_xor_sync(0xffffffffu, sm[j], o));
+              s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+            }
+            if (q == 0) ms->rowinfo[16 * cw + 2 * j + hi] = (tc_bf16_up(sm[j]) << 16) | tc_bf16_up(s2[j]);
+          }
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ms->x_empty[st]);                                       // staging stage may be refilled
+          mbar_arrive_cluster(cluster_map(smem_u32(&ms->a_full[kc]), 0));      // leader: this warp's 16 rows of chunk kc are in
+        }
+        if (cw == 0) TC_EV(1, 2, it * 16 + kc);
+      }
+    }
+  } else {
+    // ============================================================== warpgroups 2-3: scores -> candidates -> exact re-rank -> ids
+    tc_setmaxnreg_inc<176>();
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+    const int sub = (warp - (4 + TC_NCONV_WARPS)) >> 2; // which 64 of the 128 columns
+    const int rowgrp = quarter & 1, chalf = quarter >> 1;
+    const int r_local = rowgrp * 32 + lane;
+    const int cb = tc64_code_base(quarter, sub);        // first code this thread scores
+    const bool owner = (chalf == 0 && sub == 0);
+    const int slot = chalf * 2 + sub - 1;               // partner slot 0..2 (unused by the owner)
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int bar_x = 2 + rowgrp;       // partners -> owner: exch[] written
+    const int bar_m = 4 + rowgrp;       // owner -> partners: thr[] / many_word written
+    const int bar_k = 6 + rowgrp;       // partners -> owner: mask[] words written (only when many_word != 0)
+    const int bar_i = 8 + rowgrp;       // owner -> partners: the level's id is final
+    const int D = p.D;
+    const int lane4 = lane * 4;
+    uint32_t g = 0, it = 0;
+    TC_EV_DECL();
+    const int ev_role = 2 + sub;        // lane quarter 0 only
+    auto release_tmem = [&](uint32_t buf) {   // one arrive per warp on the LEADER's barrier
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->t_empty[buf]), 0));
+    };
+#pragma unroll 1
+    for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+      const int tile = 2 * unit + (int)crank;
+      const int row = tile * TC64_BM + r_local;
+      const bool valid = row < p.B;    // rows past B run the same code on zero scores; nothing of theirs is stored
+      uint64_t idpack = 0;             // 8 bits per level
+      float x4s = 0.f, x2s = 0.f;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l, ++g) {
+        const uint32_t buf = g % TC64_NBUF, u = g / TC64_NBUF;
+        const int tri = l * (l - 1) / 2;
+        auto grow = [&](int j) -> const float* {
+          return p.gram + ((size_t)(tri + j) * TC_K + (size_t)((idpack >> (8 * j)) & 0xff)) * TC_K;
+        };
+        const float* trow0 = (l >= 1) ? grow(0) : p.hcc;
+        const float* trow1 = (l >= 2) ? grow(1) : trow0;
+        auto load_t = [&](float4 (&ta)[4], float4 (&tb)[4], int col) {      // issue only: nothing here waits for data
+#pragma unroll
+          for (int v = 0; v < 4; v += 2) ldg256_pinned(trow0 + col + 4 * v, ta[v], ta[v + 1]);
+          if (l >= 2) {
+#pragma unroll
+            for (int v = 0; v < 4; v += 2) ldg256_pinned(trow1 + col + 4 * v, tb[v], tb[v + 1]);
+          }
+        };
+        auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {
+          if (l >= 2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
+#pragma unroll 1
+            for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
+              const float* gj = grow(j) + col;
+#pragma unroll
+              for (int v = 0; v < 4; v += 2) {
+                float4 t0, t1;
+                ldg256_pinned(gj + 4 * v, t0, t1);
+                ta[v].x += t0.x; ta[v].y += t0.y; ta[v].z += t0.z; ta[v].w += t0.w;
+                ta[v + 1].x += t1.x; ta[v + 1].y += t1.y; ta[v + 1].z += t1.z; ta[v + 1].w += t1.w;
+              }
+            }
+          }
+        };
+        float4 ta0[4], tb0[4], ta1[4], tb1[4];
+        load_t(ta0, tb0, cb);            // in flight across the accumulator wait below
+        mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
+        if (quarter == 0) TC_EV(ev_role, 1, it * 16 + l);
+        tc_fence_after();
+        const uint32_t tcol = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * 64;
+        uint32_t s0[16], s1[16];
+        tc_ld16_issue(tcol, s0);
+        const TcLevelConst lc = p.hdr->lv[l];
+        if (l == 0 && owner) {           // only the merging warp needs the margin
+          const uint32_t ri = ms->rowinfo[r_local];
+          const float xmax = __uint_as_float(ri & 0xffff0000u);        // max|x| (bf16, rounded up)
+          x2s = __uint_as_float(ri << 16);                              // sum x^2 (bf16, rounded up; NaN if any input is)
+          x4s = (xmax * p.sx < 65504.f) ? xmax * xmax * x2s : INFINITY;  // sum x^4 <= max|x|^2 sum x^2; fp16 overflow/inf -> poison
+          mbar_arrive(&ms->rowinfo_free);
+        }
+        // ---- margin (DESIGN.md "filter error bound"), identical to rq_tc_kernel
+        const float x2n = sqrtf(x2s);
+        const float sig = 4.8828125e-4f * 0.81649658f * sqrtf(sqrtf(x4s) * lc.c4max);          // u=2^-11, sqrt(2/3)
+        const float flo = 2.98023224e-8f * (lc.c1max / p.sx + sqrtf((float)p.D) * x2n / lc.sc);  // fp16 subnormal floor
+        const float acc = 7.62939453e-6f * x2n * lc.c2max;                                      // 64 * 2^-23 accumulate
+        const float eps = TC_Z * sig + flo + acc + lc.gerr;
+        const float margin = 2.f * eps;
+        const float ninv = -1.f / (p.sx * lc.sc);
+
+        float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+        int i1 = 0, i2 = 0;
+        auto score16 = [&](const uint32_t (&s)[16], const float4 (&t)[4], int col) {
+          if (p.one) {   // opaque always-true branch = basic-block boundary (see rq_tc.cu: keeps the prefetches early in SASS)
+            float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
+              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+            }
+            tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
+          }
+        };
+        fold_t(ta0, tb0, cb);
+        // software pipeline over the thread's 64 columns, two 16-column chunks per trip (same body as rq_tc_kernel)
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          load_t(ta1, tb1, cb + c + 16);
+          tc_ld_wait();                                   // s0 landed
+          tc_ld16_issue(tcol + c + 16, s1);
+          score16(s0, ta0, cb + c);
+          fold_t(ta1, tb1, cb + c + 16);
+          load_t(ta0, tb0, cb + 32);                      // the last trip harmlessly re-fetches chunk 32 (no branch: see rq_tc.cu)
+          tc_ld_wait();                                   // s1 landed
+          tc_ld16_issue(tcol + 32, s0);
+          score16(s1, ta1, cb + c + 16);
+          fold_t(ta0, tb0, cb + 32);
+        }
+        tc_ld_wait();
+        if (quarter == 0) TC_EV(ev_role, 2, it * 16 + l);
+
+        // exact candidate bitmask of this warp's 64 columns for the rows of the group with >= 3 candidates (warp-uniform
+        // call: tcgen05.ld is .aligned); rows that are not `many` skip the global store only
+        auto many_mask = [&](float thr, bool is_many) {
+          const uint32_t tall = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * 64;
+#pragma unroll 1
+          for (int w = 0; w < 2; ++w) {
+            uint32_t mw = 0;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              const int c = w * 32 + hh * 16;
+              tc_ld16_issue(tall + c, s0);
+              load_t(ta0, tb0, cb + c);
+              fold_t(ta0, tb0, cb + c);
+              tc_ld_wait();
+              uint32_t bits = 0;
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 0]), ninv, ta0[v].x) > thr)) << (v * 4 + 0);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 1]), ninv, ta0[v].y) > thr)) << (v * 4 + 1);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 2]), ninv, ta0[v].z) > thr)) << (v * 4 + 2);
+                bits |= (uint32_t)(!(fmaf(__uint_as_float(s0[v * 4 + 3]), ninv, ta0[v].w) > thr)) << (v * 4 + 3);
+              }
+              mw |= bits << (hh * 16);
+            }
+            if (is_many) ms->mask[r_local][(cb >> 5) + w] = mw;
+          }
+        };
+
+        if (!owner) {
+          // ---- hand this warp's top-3 to the owner, then follow its verdict
+          TcExch e; e.m1 = m1; e.m2 = m2; e.m3 = m3; e.idx = (uint32_t)i1 | ((uint32_t)i2 << 8);
+          ms->exch[slot][r_local] = e;
+          tc64_grp_arrive(bar_x);
+          tc64_grp_sync(bar_m);
+          const uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->many_word[rowgrp]);
+          if (mw) {
+            many_mask(*reinterpret_cast<volatile float*>(&ms->thr[r_local]), (mw >> lane) & 1);
+            tc64_grp_arrive(bar_k);
+          }
+          release_tmem(buf);
+          tc64_grp_sync(bar_i);
+          if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
+          idpack |= (uint64_t)(*reinterpret_cast<volatile uint32_t*>(&ms->idpub[r_local]) & 0xff) << (8 * l);
+          continue;
+        }
+
+        tc64_grp_sync(bar_x);
+#pragma unroll
+        for (int sidx = 0; sidx < 3; ++sidx) {
+          const TcExch e = ms->exch[sidx][r_local];
+          tc_insert(e.m1, (int)(e.idx & 0xff), m1, m2, m3, i1, i2);
+          tc_insert(e.m2, (int)((e.idx >> 8) & 0xff), m1, m2, m3, i1, i2);
+          m3 = fminf(m3, fmaxf(m2, e.m3));
+        }
+        const float thr = tcs_threshold(m1, margin);
+        const bool flagged = valid && !(m2 > thr);          // >= 2 candidates (NaN/inf margins land here too)
+        const bool many = flagged && !(m3 > thr);           // >= 3 candidates: rare, needs the full candidate mask
+        const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
+        const uint32_t mn = __ballot_sync(0xffffffffu, many);
+        ms->thr[r_local] = thr;
+        if (lane == 0) ms->many_word[rowgrp] = mn;
+        tc64_grp_arrive(bar_m);
+        if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
+        if (mn) {
+          many_mask(thr, many);
+          tc64_grp_sync(bar_k);          // the partners' mask words are in
+        }
+        release_tmem(buf);
+        if (quarter == 0) TC_EV(ev_role, 4, it * 16 + l);
+
+        int my_id = i1;
+        // ---- warp-cooperative exact re-rank of the flagged rows: identical arithmetic to rq_tc_kernel / rq_simt.cu
+        // (sequential fp32 residual, (xx + cc) - 2 dot, first index wins ties)
+        const float* ccl = p.cc + l * TC_K;
+        const float* cl = p.cbf + (size_t)l * TC_K * D;
+        uint32_t todo = fl;
+        int n_cand = 0;
+        auto ld_row = [&](const float* base, float4 (&v)[6]) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            v[i] = (i * 128 + lane4 < D) ? __ldg(reinterpret_cast<const float4*>(base + i * 128 + lane4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+#pragma unroll 1
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int rrow = __shfl_sync(0xffffffffu, row, src);
+          const uint32_t idlo = __shfl_sync(0xffffffffu, (uint32_t)idpack, src);
+          const uint32_t idhi = __shfl_sync(0xffffffffu, (uint32_t)(idpack >> 32), src);
+          const uint64_t rid = ((uint64_t)idhi << 32) | idlo;
+          const int ci1 = __shfl_sync(0xffffffffu, i1, src), ci2 = __shfl_sync(0xffffffffu, i2, src);
+          const bool is_many = (mn >> src) & 1;
+          const int ka = min(ci1, ci2), kb = max(ci1, ci2);
+          float4 res[6], ev[6], va[6], vb[6];
+          ld_row(p.x + (int64_t)rrow * p.ldx, res);        // this kernel is only launched on 16-byte aligned rows
+          ld_row(cl + (size_t)ka * D, va);
+          ld_row(cl + (size_t)kb * D, vb);
+#pragma unroll 1
+          for (int j = 0; j < l; ++j) {
+            ld_row(p.cbf + ((size_t)j * TC_K + (size_t)((rid >> (8 * j)) & 0xff)) * D, ev);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { res[i].x -= ev[i].x; res[i].y -= ev[i].y; res[i].z -= ev[i].z; res[i].w -= ev[i].w; }   // rqvae.py:130, level order
+          }
+          float xx = 0.f;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) xx = tc_dot4(res[i], res[i], xx);
+          xx = warp_sum(xx);
+          float best = INFINITY;
+          int besti = 0x7fffffff;
+          if (!is_many) {
+            float da = 0.f, db = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { da = tc_dot4(res[i], va[i], da); db = tc_dot4(res[i], vb[i], db); }
+            da = warp_sum(da);
+            db = warp_sum(db);
+            const float dist_a = (xx + __ldg(ccl + ka)) - 2.f * da;             // quantize.py:113-117
+            const float dist_b = (xx + __ldg(ccl + kb)) - 2.f * db;
+            best = dist_a; besti = ka;
+            if (dist_b < best) { best = dist_b; besti = kb; }
+            if (!(dist_a == dist_a)) besti = (dist_b == dist_b) ? kb : ci1;     // NaN distances: keep something valid
+            n_cand += 2;
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+              uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->mask[rowgrp * 32 + src][c]);
+#pragma unroll 1
+              while (mw) {
+                const int k = c * 32 + __ffs(mw) - 1;
+                mw &= mw - 1;
+                ld_row(cl + (size_t)k * D, va);
+                float dot = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) dot = tc_dot4(res[i], va[i], dot);
+                dot = warp_sum(dot);
+                const float dist = (xx + __ldg(ccl + k)) - 2.f * dot;
+                if (dist < best) { best = dist; besti = k; }
+                ++n_cand;
+              }
+            }
+            if (besti > 255) besti = ci1;   // all-NaN row: keep the filter's pick
+          }
+          if (lane == src) my_id = besti;
+        }
+        if (p.stats && lane == 0 && fl) {
+          atomicAdd(p.stats + 0, __popc(fl));
+          atomicAdd(p.stats + 1, n_cand);
+          atomicAdd(p.stats + 2, __popc(mn));
+        }
+        idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
+        ms->idpub[r_local] = (uint32_t)my_id;     // publish the final id of this level to the partner warps
+        tc64_grp_arrive(bar_i);
+        if (quarter == 0) TC_EV(ev_role, 5, it * 16 + l);
+        if (valid) p.ids[(int64_t)row * L + l] = my_id;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                // neither CTA may exit (or free TMEM) while the other can still reach into it
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc2(TC64_TMEM_BASE(), 512);
+  }
+}
+
+template <bool kTrace>
+static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kern = rq_tc64_kernel<kTrace>;
+  RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  RQB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}
+
+// p: everything filled in by rqb200_tokenize_tc_run except the tensor maps.  Requires 16-byte aligned rows (x & 15 == 0,
+// ldx % 4 == 0): the tensor map over x needs it, and the caller routes other inputs to rq_tc_kernel.
+int tc64_run(TcParams& p, int sm_count, bool trace, cudaStream_t st) {
+  int rc = tc_encode_blob_map(&p.tmapB, p.blob, p.L * 2 * p.nkc);
+  if (rc) return rc;
+  rc = tc_encode_2d(&p.tmapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.x, (uint64_t)p.D, (uint64_t)p.B, (uint64_t)p.ldx * 4,
+                    TC_KC, TC64_BM);
+  if (rc) return rc;
+  const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
+  const int units = (ntiles64 + 1) / 2;
+  const int nclusters = units < sm_count / 2 ? units : sm_count / 2;
+  const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)TC64_NB * TC_BSTAGE_BYTES +
+                      (size_t)TC64_NX * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
+  return trace ? tc64_launch<true>(p, 2 * nclusters, smem, st) : tc64_launch<false>(p, 2 * nclusters, smem, st);
+}

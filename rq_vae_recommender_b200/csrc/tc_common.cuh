@@ -179,6 +179,7 @@ struct TcParams {
   int rot;              // 1: every CTA walks the k chunks from its own starting chunk (blockIdx % nkc), see tc_rot()
   int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
   int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
+  CUtensorMap tmapX;    // rq_tc64_kernel only: x as a [B][D] fp32 tensor, box = 64 rows x 64 floats (one 16 KB staging stage)
 };
 
 struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
@@ -245,3 +246,42 @@ __device__ __forceinline__ int tc_rot(int i, int rot0, int nkc) {
 __device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda): a row-major 2-D tensor, no swizzle,
+// out-of-bounds elements read as zero
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline int tc_encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t dim0, uint64_t dim1,
+                               uint64_t stride1_bytes, uint32_t box0, uint32_t box1) {
+  static TcEncodeFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RQB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+    if (!f || q != cudaDriverEntryPointSuccess) {
+      rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return RQB_ERR_UNSUPPORTED;
+    }
+    fn = reinterpret_cast<TcEncodeFn>(f);
+  }
+  const cuuint64_t gdim[2] = {dim0, dim1};
+  const cuuint64_t gstr[1] = {stride1_bytes};
+  const cuuint32_t box[2] = {box0, box1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    rqb_set_error("tokenize_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RQB_ERR_CUDA;
+  }
+  return RQB_OK;
+}
+// the fp16 codebook blob is a sequence of pre-swizzled 16 KB images = 128 rows of 128 bytes each: a [nblocks*128][64] fp16
+// matrix whose box {64, 128} is exactly one image; no swizzle here, the bytes are already in the tcgen05 shared-memory order
+static inline int tc_encode_blob_map(CUtensorMap* tm, const void* blob, int nblocks) {
+  return tc_encode_2d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, blob, 64, (uint64_t)nblocks * 128, 128, 64, 128);
+}
+
+// rq_tc64.cu: the 64-rows-per-CTA kernel (M = 128 CTA-pair MMAs, x staged by TMA).  `p` carries everything but tmapX / tmapB.
+int tc64_run(TcParams& p, int sm_count, bool trace, cudaStream_t st);

@@ -155,3 +155,42 @@ def test_cta_pair_variant_returns_the_same_ids(tmp_path):
         ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs]).cpu().numpy()
         pair = np.load(tmp_path / f"pair_{B}_{D}_{L}.npy")
         assert np.array_equal(ids, pair), (B, D, L, int((ids != pair).any(axis=1).sum()))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("RQB200_TEST_UNVALIDATED", "0") != "1",
+                    reason="rq_tc64_kernel (RQB200_TC_64=1) was written without GPU access at the end of round 1 and has not run "
+                           "on hardware yet: bring it up with tools/pair64_probe.cu first, then set RQB200_TEST_UNVALIDATED=1")
+def test_tc64_variant_returns_the_same_ids(tmp_path):
+    """The opt-in 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M=128 CTA-pair MMAs, x staged by tensor-map TMA) must return
+    exactly the ids of the default kernel: odd 64-row tile counts (the pair's second CTA past the end), a partial last
+    tile (TMA zero fill), strided rows, and inputs that force the `many` path (exact duplicates among the codes)."""
+    import os, subprocess, sys
+    from rq_vae_recommender_b200 import ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shapes = [(1, 768, 3), (65, 768, 3), (129, 768, 3), (513, 256, 4), (1000, 768, 3), (20000, 768, 3), (600, 64, 8)]
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests', 'golden')!r})\n"
+        "import inputs as I\n"
+        "from rq_vae_recommender_b200 import ops\n"
+        f"for (B, D, L) in {shapes!r}:\n"
+        "    x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D); x = x[:B]\n"
+        "    if B == 513:\n"
+        "        cbs[0][200] = cbs[0][17]; cbs[0][90] = cbs[0][17]; x[:64] = cbs[0][17] + 1e-4 * x[:64]\n"
+        "    ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs])\n"
+        f"    np.save({str(tmp_path)!r} + f'/tc64_{{B}}_{{D}}_{{L}}.npy', ids.cpu().numpy())\n"
+        "print('TC64 DONE')\n"
+    )
+    env = dict(os.environ, RQB200_TC_64="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "TC64 DONE" in res.stdout, res.stdout + res.stderr
+    assert os.environ.get("RQB200_TC_64", "0") != "1", "run this test with the default kernel in the parent process"
+    for (B, D, L) in shapes:
+        x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D)
+        x = x[:B]
+        if B == 513:
+            cbs[0][200] = cbs[0][17]; cbs[0][90] = cbs[0][17]; x[:64] = cbs[0][17] + 1e-4 * x[:64]
+        ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs]).cpu().numpy()
+        got = np.load(tmp_path / f"tc64_{B}_{D}_{L}.npy")
+        assert np.array_equal(ids, got), (B, D, L, int((ids != got).any(axis=1).sum()))
