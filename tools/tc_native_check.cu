@@ -1,0 +1,94 @@
+// Python-free harness around the C ABI's tensor-core tokeniser (include/rqb200.h: rqb200_tokenize_tc_prepare / _run):
+// seeded synthetic unit-norm rows and live codebooks, one run whose ids go to a file, then `iters` event-timed runs.
+// The kernel variant is chosen by the library's environment switches (RQB200_TC_64, RQB200_TC_PAIR), which are read once
+// per process -- so variants are compared by running this binary once per setting and `cmp`-ing the id files:
+//   tools/bin/tc_native_check 65536 768 3 20 /tmp/a.ids;  RQB200_TC_64=1 tools/bin/tc_native_check 65536 768 3 20 /tmp/b.ids;  cmp /tmp/a.ids /tmp/b.ids
+// A fresh GPU box spends about a minute importing torch; this starts in milliseconds, which matters when GPU time is short.
+// build: nvcc -O2 -std=c++17 -o tools/bin/tc_native_check tools/tc_native_check.cu -ldl      (run from the repo root)
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 2; } } while (0)
+
+typedef size_t (*StateBytesFn)(int, int, int);
+typedef int (*PrepareFn)(const float* const*, int, int, int, void*, size_t, void*);
+typedef int (*RunFn)(const float*, int64_t, int, const void*, int, int, int, int64_t*, int*, void*);
+typedef const char* (*ErrFn)();
+
+static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+static inline float urand() {   // xorshift64*, uniform in [0,1)
+  rng_state ^= rng_state >> 12; rng_state ^= rng_state << 25; rng_state ^= rng_state >> 27;
+  return (float)((rng_state * 0x2545F4914F6CDD1Dull) >> 40) / 16777216.0f;
+}
+static inline float grand() { return sqrtf(-2.f * logf(urand() + 1e-12f)) * cosf(6.2831853f * urand()); }
+
+int main(int argc, char** argv) {
+  const int B = argc > 1 ? atoi(argv[1]) : 65536, D = argc > 2 ? atoi(argv[2]) : 768, L = argc > 3 ? atoi(argv[3]) : 3;
+  const int iters = argc > 4 ? atoi(argv[4]) : 20;
+  const char* out = argc > 5 ? argv[5] : nullptr;
+  const int K = 256;
+  void* lib = dlopen("rq_vae_recommender_b200/librqb200.so", RTLD_NOW);
+  if (!lib) { printf("dlopen failed: %s\n", dlerror()); return 2; }
+  auto state_bytes = (StateBytesFn)dlsym(lib, "rqb200_tokenize_tc_state_bytes");
+  auto prepare = (PrepareFn)dlsym(lib, "rqb200_tokenize_tc_prepare");
+  auto run = (RunFn)dlsym(lib, "rqb200_tokenize_tc_run");
+  auto last_error = (ErrFn)dlsym(lib, "rqb200_last_error");
+  if (!state_bytes || !prepare || !run || !last_error) { printf("missing symbol\n"); return 2; }
+
+  std::vector<float> x((size_t)B * D);
+  for (int b = 0; b < B; ++b) {
+    double n2 = 0;
+    for (int d = 0; d < D; ++d) { const float v = grand(); x[(size_t)b * D + d] = v; n2 += (double)v * v; }
+    const float inv = (float)(1.0 / sqrt(n2));
+    for (int d = 0; d < D; ++d) x[(size_t)b * D + d] *= inv;
+  }
+  // level 0: rows of x plus noise (all codes live); level l: residual-sized random directions
+  std::vector<std::vector<float>> cbs(L, std::vector<float>((size_t)K * D));
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < K; ++k) {
+      const size_t src = ((size_t)k * 2654435761u + l * 97u) % (size_t)B;
+      const float s = l == 0 ? 1.f : 0.f, noise = (l == 0 ? 0.3f : 0.7f / (float)l) / sqrtf((float)D);
+      for (int d = 0; d < D; ++d) cbs[l][(size_t)k * D + d] = s * x[src * D + d] + noise * grand();
+    }
+  float* dx; int64_t* dids; int* dstats; void* dstate;
+  std::vector<float*> dcb(L);
+  CK(cudaMalloc(&dx, x.size() * 4)); CK(cudaMalloc(&dids, (size_t)B * L * 8)); CK(cudaMalloc(&dstats, 64 * 4));
+  CK(cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dids, 0xff, (size_t)B * L * 8)); CK(cudaMemset(dstats, 0, 64 * 4));
+  for (int l = 0; l < L; ++l) {
+    CK(cudaMalloc(&dcb[l], (size_t)K * D * 4));
+    CK(cudaMemcpy(dcb[l], cbs[l].data(), (size_t)K * D * 4, cudaMemcpyHostToDevice));
+  }
+  const size_t sb = state_bytes(D, K, L);
+  if (!sb) { printf("shape not supported\n"); return 2; }
+  CK(cudaMalloc(&dstate, sb));
+  if (prepare(dcb.data(), D, K, L, dstate, sb, nullptr)) { printf("prepare failed: %s\n", last_error()); return 1; }
+  if (run(dx, D, B, dstate, D, K, L, dids, dstats, nullptr)) { printf("run failed: %s\n", last_error()); return 1; }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("first run: %s\n", cudaGetErrorString(se)); return 1; }
+  std::vector<int64_t> ids((size_t)B * L);
+  int stats[4];
+  CK(cudaMemcpy(ids.data(), dids, ids.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(stats, dstats, 16, cudaMemcpyDeviceToHost));
+  long bad = 0; uint64_t h = 1469598103934665603ull;
+  for (int64_t v : ids) { if (v < 0 || v >= K) ++bad; h = (h ^ (uint64_t)v) * 1099511628211ull; }
+  if (out) { FILE* f = fopen(out, "wb"); if (f) { fwrite(ids.data(), 8, ids.size(), f); fclose(f); } }
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) run(dx, D, B, dstate, D, K, L, dids, nullptr, nullptr);
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) run(dx, D, B, dstate, D, K, L, dids, nullptr, nullptr);
+  CK(cudaEventRecord(e1));
+  se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("timed runs: %s\n", cudaGetErrorString(se)); return 1; }
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  const char* v64 = getenv("RQB200_TC_64"); const char* vp = getenv("RQB200_TC_PAIR");
+  printf("B=%d D=%d L=%d TC_64=%s TC_PAIR=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
+         B, D, L, v64 ? v64 : "-", vp ? vp : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
+         B / (ms / iters) * 1e-3);
+  return bad ? 1 : 0;
+}
