@@ -38,6 +38,7 @@
 struct Tc64Misc {
   uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
   uint64_t b_full[TC64_NB], b_empty[TC64_NB];
+  uint64_t b_peer[TC64_NB];       // kCl = 4 only, pair leader: the peer CTA's codebook stage has landed (forwarded)
   uint64_t x_full[TC64_NX], x_empty[TC64_NX];
   uint64_t t_full[TC64_NBUF], t_empty[TC64_NBUF];
   uint64_t rowinfo_free;
@@ -57,6 +58,18 @@ __device__ __forceinline__ void tc64_tma2d(void* smem_dst, const CUtensorMap* tm
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, delivered to the same shared-memory offset (data and mbarrier) of every CTA whose bit is set in `mask`
+__device__ __forceinline__ void tc64_tma2d_mc(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// completion of all prior tcgen05 ops of this thread -> the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 // named barriers of one row group (4 warps = 128 threads)
 __device__ __forceinline__ void tc64_grp_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc64_grp_arrive(int id) {
@@ -64,7 +77,10 @@ __device__ __forceinline__ void tc64_grp_arrive(int id) {
   asm volatile("bar.arrive %0, 128;" ::"r"(id) : "memory");
 }
 
-template <bool kTrace>
+// kCl = cluster size.  2: one CTA pair per cluster, every pair streams the codebook blocks from L2 by itself.
+// 4: two pairs per cluster share every block: each of the two CTAs that need a given 16 KB half-block loads one 8 KB slice
+// of it and multicasts it to both (half the L2 reads per row; the pairs couple only through the depth of the B ring).
+template <bool kTrace, int kCl>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                             // [TC_MAX_KC][8 KB]
@@ -75,16 +91,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
   const bool trace = kTrace && p.stats != nullptr;
-  const uint32_t crank = cluster_ctarank();                           // 0 = leader
-  // work unit = pair-tile of 128 rows (one cluster); this CTA takes the 64-row tile 2 * unit + crank
-  const int u_first = (int)(blockIdx.x >> 1), u_step = (int)(gridDim.x >> 1);
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = rank & 1u;                                   // rank inside the CTA pair, 0 = its leader
+  const uint32_t leader = rank & ~1u;                                 // cluster rank of this pair's leader
+  const uint32_t pair = rank >> 1;                                    // which pair of the cluster (0 when kCl == 2)
+  const uint16_t pair_mask = (uint16_t)(3u << leader);                // both CTAs of this pair
+  // work unit = kCl consecutive 64-row tiles (one cluster); this CTA takes tile kCl * unit + rank
+  const int u_first = (int)(blockIdx.x / kCl), u_step = (int)(gridDim.x / kCl);
   const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
-  const int u_count = (ntiles64 + 1) >> 1;
+  const int u_count = (ntiles64 + kCl - 1) / kCl;
 
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
     for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], 2 * TC_NCONV_WARPS); mbar_init(&ms->a_empty[i], 1); }
-    for (int i = 0; i < TC64_NB; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
+    for (int i = 0; i < TC64_NB; ++i) {
+      mbar_init(&ms->b_full[i], 1);
+      mbar_init(&ms->b_empty[i], kCl / 2);   // one multicast commit per pair leader that reads the (shared) stage
+      mbar_init(&ms->b_peer[i], 1);
+    }
     for (int i = 0; i < TC64_NX; ++i) { mbar_init(&ms->x_full[i], 1); mbar_init(&ms->x_empty[i], TC_NCONV_WARPS); }
     for (int i = 0; i < TC64_NBUF; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS); }
     mbar_init(&ms->rowinfo_free, TC64_BM);       // the owner thread of every row
@@ -108,16 +132,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         for (int l = 0; l < L; ++l)
           for (int kc = 0; kc < nkc; ++kc, ++s) {
             const uint32_t st = s % TC64_NB, u = s / TC64_NB;
-            mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);      // local: the leader's commits are multicast
+            mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);      // local: the leaders' commits are multicast
             if (tc_elect_one()) {
-              if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
-              tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, ((l * 2 + (int)crank) * nkc + kc) * 128,
-                            cluster_map(smem_u32(&ms->b_full[st]), 0));
+              const int blk_row = ((l * 2 + (int)crank) * nkc + kc) * 128;      // first blob row of this CTA's half-block
+              if constexpr (kCl == 2) {
+                if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
+                tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, blk_row, cluster_map(smem_u32(&ms->b_full[st]), 0));
+              } else {
+                // this CTA and the CTA of the other pair with the same pair-rank need the same half-block: each loads the
+                // 64-row slice `pair` of it and multicasts it to both; every CTA arms its OWN b_full for the 16 KB it receives
+                // (a slice may land before the receiver has armed this phase: the pending arrival keeps the phase open)
+                mbar_expect_tx(&ms->b_full[st], TC_BSTAGE_BYTES);
+                tc64_tma2d_mc(sB + st * TC_BSTAGE_BYTES + pair * (TC_BSTAGE_BYTES / 2), &p.tmapB2, 0, blk_row + (int)pair * 64,
+                              &ms->b_full[st], (uint16_t)(5u << crank));
+              }
             }
             __syncwarp();
           }
     } else if (warp == 1 && crank == 0) {
       const uint32_t idesc = tc_idesc(128, 256);
+      const uint16_t all_mask = (uint16_t)((1u << kCl) - 1u);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t s = 0, g = 0, it = 0;
       TC_EV_DECL();
@@ -135,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
             }
             const uint32_t st = s % TC64_NB;
             mbar_wait_guarded_cluster(&ms->b_full[st], (s / TC64_NB) & 1, 4);
+            if constexpr (kCl == 4) mbar_wait_guarded_cluster(&ms->b_peer[st], (s / TC64_NB) & 1, 10);
             tc_fence_after();
             const uint64_t adesc = tc_smem_desc(a_base + kc * TC64_ACHUNK_BYTES);
             const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
@@ -142,9 +177,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < TC_KC / 16; ++j)   // K=16 per instruction: +32 B inside the 128 B swizzle row
                 tc_mma_f16_2(d_tmem, adesc + 2 * j, bdesc + 2 * j, idesc, (kc | j) != 0);
-              tc_commit2(&ms->b_empty[st]);
-              if (l == L - 1) tc_commit2(&ms->a_empty[kc]);
-              if (kc == nkc - 1) tc_commit2(&ms->t_full[buf]);
+              tc64_commit_mask(&ms->b_empty[st], all_mask);       // every CTA whose producer writes into a stage we read
+              if (l == L - 1) tc64_commit_mask(&ms->a_empty[kc], pair_mask);
+              if (kc == nkc - 1) tc64_commit_mask(&ms->t_full[buf], pair_mask);
             }
             __syncwarp();
           }
@@ -155,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
       // CTA past the last 64-row tile loads the last tile again (its scores are never stored).
       uint32_t s = 0;
       for (int unit = u_first; unit < u_count; unit += u_step) {
-        const int tile = min(2 * unit + (int)crank, ntiles64 - 1);
+        const int tile = min(kCl * unit + (int)rank, ntiles64 - 1);
         for (int kc = 0; kc < nkc; ++kc, ++s) {
           const uint32_t st = s % TC64_NX, u = s / TC64_NX;
           mbar_wait_guarded(&ms->x_empty[st], (u & 1) ^ 1, 8);
@@ -166,6 +201,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           __syncwarp();
         }
       }
+    } else if (kCl == 4 && warp == 3 && crank == 1) {
+      // the leader's MMA warp reads the codebook stage of BOTH CTAs of the pair; with multicast loads each CTA's bytes are
+      // counted on its own b_full, so the peer forwards every completed phase to the leader
+      uint32_t s = 0;
+      for (int unit = u_first; unit < u_count; unit += u_step)
+        for (int i = 0; i < L * nkc; ++i, ++s) {
+          const uint32_t st = s % TC64_NB;
+          mbar_wait_guarded(&ms->b_full[st], (s / TC64_NB) & 1, 11);
+          if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->b_peer[st]), leader));
+          __syncwarp();
+        }
     }
   } else if (warp < 4 + TC_NCONV_WARPS) {
     // ============================================================== warpgroup 1: fp32 staging -> fp16 swizzled A chunks
@@ -215,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&ms->x_empty[st]);                                       // staging stage may be refilled
-          mbar_arrive_cluster(cluster_map(smem_u32(&ms->a_full[kc]), 0));      // leader: this warp's 16 rows of chunk kc are in
+          mbar_arrive_cluster(cluster_map(smem_u32(&ms->a_full[kc]), leader)); // pair leader: this warp's 16 rows of chunk kc are in
         }
         if (cw == 0) TC_EV(1, 2, it * 16 + kc);
       }
@@ -243,11 +289,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     auto release_tmem = [&](uint32_t buf) {   // one arrive per warp on the LEADER's barrier
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->t_empty[buf]), 0));
+      if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->t_empty[buf]), leader));
     };
 #pragma unroll 1
     for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
-      const int tile = 2 * unit + (int)crank;
+      const int tile = kCl * unit + (int)rank;
       const int row = tile * TC64_BM + r_local;
       const bool valid = row < p.B;    // rows past B run the same code on zero scores; nothing of theirs is stored
       uint64_t idpack = 0;             // 8 bits per level
@@ -510,9 +556,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
   }
 }
 
-template <bool kTrace>
+template <bool kTrace, int kCl>
 static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = rq_tc64_kernel<kTrace>;
+  auto kern = rq_tc64_kernel<kTrace, kCl>;
   RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -521,7 +567,7 @@ static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = kCl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   RQB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
@@ -531,16 +577,43 @@ static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st
 
 // p: everything filled in by rqb200_tokenize_tc_run except the tensor maps.  Requires 16-byte aligned rows (x & 15 == 0,
 // ldx % 4 == 0): the tensor map over x needs it, and the caller routes other inputs to rq_tc_kernel.
-int tc64_run(TcParams& p, int sm_count, bool trace, cudaStream_t st) {
-  int rc = tc_encode_blob_map(&p.tmapB, p.blob, p.L * 2 * p.nkc);
+int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st) {
+  const int nblocks = p.L * 2 * p.nkc;
+  int rc = tc_encode_blob_map(&p.tmapB, p.blob, nblocks);
+  if (rc) return rc;
+  rc = tc_encode_2d(&p.tmapB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.blob, 64, (uint64_t)nblocks * 128, 128, 64, 64);   // 8 KB slices
   if (rc) return rc;
   rc = tc_encode_2d(&p.tmapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.x, (uint64_t)p.D, (uint64_t)p.B, (uint64_t)p.ldx * 4,
                     TC_KC, TC64_BM);
   if (rc) return rc;
   const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
-  const int units = (ntiles64 + 1) / 2;
-  const int nclusters = units < sm_count / 2 ? units : sm_count / 2;
   const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)TC64_NB * TC_BSTAGE_BYTES +
                       (size_t)TC64_NX * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
-  return trace ? tc64_launch<true>(p, 2 * nclusters, smem, st) : tc64_launch<false>(p, 2 * nclusters, smem, st);
+  if (cluster == 4 && ntiles64 > 2) {
+    // how many clusters of 4 CTAs (one per SM at this shared-memory size) the device can hold at once: GPC boundaries make
+    // this less than sm_count / 4 (queried, not assumed)
+    static int max4 = -1;
+    if (max4 < 0) {
+      auto kern = rq_tc64_kernel<false, 4>;
+      RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(sm_count / 4 * 4));
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      RQB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max4 = n > 0 ? n : 1;
+    }
+    const int units = (ntiles64 + 3) / 4;
+    const int ncl = units < max4 ? units : max4;
+    return trace ? tc64_launch<true, 4>(p, 4 * ncl, smem, st) : tc64_launch<false, 4>(p, 4 * ncl, smem, st);
+  }
+  const int units = (ntiles64 + 1) / 2;
+  const int nclusters = units < sm_count / 2 ? units : sm_count / 2;
+  return trace ? tc64_launch<true, 2>(p, 2 * nclusters, smem, st) : tc64_launch<false, 2>(p, 2 * nclusters, smem, st);
 }

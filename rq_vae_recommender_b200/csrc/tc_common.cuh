@@ -180,6 +180,7 @@ struct TcParams {
   int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
   int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
   CUtensorMap tmapX;    // rq_tc64_kernel only: x as a [B][D] fp32 tensor, box = 64 rows x 64 floats (one 16 KB staging stage)
+  CUtensorMap tmapB2;   // rq_tc64_kernel, clusters of 4: the codebook blob with a 64-row box (8 KB multicast slices)
 };
 
 struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
@@ -284,4 +285,5 @@ static inline int tc_encode_blob_map(CUtensorMap* tm, const void* blob, int nblo
 }
 
 // rq_tc64.cu: the 64-rows-per-CTA kernel (M = 128 CTA-pair MMAs, x staged by TMA).  `p` carries everything but tmapX / tmapB.
-int tc64_run(TcParams& p, int sm_count, bool trace, cudaStream_t st);
+// cluster = 2: one CTA pair per cluster; 4: two pairs per cluster sharing every codebook block by TMA multicast.
+int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st);

@@ -8,7 +8,9 @@ mkdir -p gpurun_out
     set -- $shape
     timeout 40 tools/bin/tc_native_check $1 $2 $3 $4 /tmp/a_$1.ids; echo "exit $?"
     RQB200_TC_64=1 timeout 40 tools/bin/tc_native_check $1 $2 $3 $4 /tmp/b_$1.ids; echo "exit $?"
-    cmp /tmp/a_$1.ids /tmp/b_$1.ids && echo "IDS_IDENTICAL B=$1"
+    cmp /tmp/a_$1.ids /tmp/b_$1.ids && echo "IDS_IDENTICAL B=$1 (clusters of 2)"
+    RQB200_TC_64=4 timeout 40 tools/bin/tc_native_check $1 $2 $3 $4 /tmp/c_$1.ids; echo "exit $?"
+    cmp /tmp/a_$1.ids /tmp/c_$1.ids && echo "IDS_IDENTICAL B=$1 (clusters of 4, multicast)"
   done
 } > gpurun_out/tc64_bringup.txt 2>&1
 cat gpurun_out/tc64_bringup.txt
