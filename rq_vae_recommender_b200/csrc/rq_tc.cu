@@ -853,8 +853,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool trace = want_trace && stats;       // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
   // 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M = 128 CTA-pair MMAs, x staged by TMA): opt-in, not yet run on hardware
-  // RQB200_TC_64=1: clusters of 2 (one pair); =4: clusters of 4 (two pairs sharing the codebook blocks by TMA multicast)
-  static const int opt_64 = []() { const char* e = getenv("RQB200_TC_64"); return (e && e[0] == '1') ? 2 : (e && e[0] == '4') ? 4 : 0; }();
+  // RQB200_TC_64=1: clusters of 2 (one pair); =4 / =8: clusters of 4 / 8 (two / four pairs sharing the codebook blocks by TMA multicast)
+  static const int opt_64 = []() { const char* e = getenv("RQB200_TC_64"); return (e && e[0] == '1') ? 2 : (e && e[0] == '4') ? 4 : (e && e[0] == '8') ? 8 : 0; }();
   if (opt_64 && vec_ok && sm_count >= opt_64) return tc64_run(p, sm_count, trace, opt_64, st);
   // CTA-pair variant (cta_group::2): opt-in while it is being brought up
   static const int opt_pair = []() { const char* e = getenv("RQB200_TC_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();

@@ -78,8 +78,8 @@ __device__ __forceinline__ void tc64_grp_arrive(int id) {
 }
 
 // kCl = cluster size.  2: one CTA pair per cluster, every pair streams the codebook blocks from L2 by itself.
-// 4: two pairs per cluster share every block: each of the two CTAs that need a given 16 KB half-block loads one 8 KB slice
-// of it and multicasts it to both (half the L2 reads per row; the pairs couple only through the depth of the B ring).
+// 4 / 8: two / four pairs per cluster share every block: each of the CTAs that need a given 16 KB half-block loads one slice
+// of it and multicasts it to all of them (1/2, 1/4 of the L2 reads per row; the pairs couple only through the B ring's depth).
 template <bool kTrace, int kCl>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
@@ -139,12 +139,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
                 if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
                 tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, blk_row, cluster_map(smem_u32(&ms->b_full[st]), 0));
               } else {
-                // this CTA and the CTA of the other pair with the same pair-rank need the same half-block: each loads the
-                // 64-row slice `pair` of it and multicasts it to both; every CTA arms its OWN b_full for the 16 KB it receives
+                // this CTA and the CTAs of the other pairs with the same pair-rank need the same half-block: each loads
+                // slice `pair` of it and multicasts it to all of them; every CTA arms its OWN b_full for the 16 KB it receives
                 // (a slice may land before the receiver has armed this phase: the pending arrival keeps the phase open)
+                constexpr int kSliceRows = 128 / (kCl / 2);             // 64 (8 KB) for clusters of 4, 32 (4 KB) for clusters of 8
                 mbar_expect_tx(&ms->b_full[st], TC_BSTAGE_BYTES);
-                tc64_tma2d_mc(sB + st * TC_BSTAGE_BYTES + pair * (TC_BSTAGE_BYTES / 2), &p.tmapB2, 0, blk_row + (int)pair * 64,
-                              &ms->b_full[st], (uint16_t)(5u << crank));
+                tc64_tma2d_mc(sB + st * TC_BSTAGE_BYTES + pair * (kSliceRows * 128), &p.tmapB2, 0, blk_row + (int)pair * kSliceRows,
+                              &ms->b_full[st], (uint16_t)((0x55u & ((1u << kCl) - 1u)) << crank));
               }
             }
             __syncwarp();
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
             }
             const uint32_t st = s % TC64_NB;
             mbar_wait_guarded_cluster(&ms->b_full[st], (s / TC64_NB) & 1, 4);
-            if constexpr (kCl == 4) mbar_wait_guarded_cluster(&ms->b_peer[st], (s / TC64_NB) & 1, 10);
+            if constexpr (kCl > 2) mbar_wait_guarded_cluster(&ms->b_peer[st], (s / TC64_NB) & 1, 10);
             tc_fence_after();
             const uint64_t adesc = tc_smem_desc(a_base + kc * TC64_ACHUNK_BYTES);
             const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           __syncwarp();
         }
       }
-    } else if (kCl == 4 && warp == 3 && crank == 1) {
+    } else if (kCl > 2 && warp == 3 && crank == 1) {
       // the leader's MMA warp reads the codebook stage of BOTH CTAs of the pair; with multicast loads each CTA's bytes are
       // counted on its own b_full, so the peer forwards every completed phase to the leader
       uint32_t s = 0;
@@ -581,7 +582,8 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
   const int nblocks = p.L * 2 * p.nkc;
   int rc = tc_encode_blob_map(&p.tmapB, p.blob, nblocks);
   if (rc) return rc;
-  rc = tc_encode_2d(&p.tmapB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.blob, 64, (uint64_t)nblocks * 128, 128, 64, 64);   // 8 KB slices
+  rc = tc_encode_2d(&p.tmapB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.blob, 64, (uint64_t)nblocks * 128, 128, 64,
+                    cluster == 8 ? 32 : 64);   // multicast slices: 8 KB (clusters of 4) or 4 KB (clusters of 8)
   if (rc) return rc;
   rc = tc_encode_2d(&p.tmapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.x, (uint64_t)p.D, (uint64_t)p.B, (uint64_t)p.ldx * 4,
                     TC_KC, TC64_BM);
@@ -589,29 +591,30 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
   const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
   const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)TC64_NB * TC_BSTAGE_BYTES +
                       (size_t)TC64_NX * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
-  if (cluster == 4 && ntiles64 > 2) {
-    // how many clusters of 4 CTAs (one per SM at this shared-memory size) the device can hold at once: GPC boundaries make
-    // this less than sm_count / 4 (queried, not assumed)
-    static int max4 = -1;
-    if (max4 < 0) {
-      auto kern = rq_tc64_kernel<false, 4>;
+  if ((cluster == 4 || cluster == 8) && ntiles64 > 2) {
+    // how many clusters of this size (one CTA per SM at this shared-memory size) the device can hold at once: GPC boundaries
+    // make this less than sm_count / cluster (queried, not assumed)
+    static int max_cl[9] = {0};
+    if (max_cl[cluster] == 0) {
+      const void* kern = cluster == 4 ? (const void*)rq_tc64_kernel<false, 4> : (const void*)rq_tc64_kernel<false, 8>;
       RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(sm_count / 4 * 4));
+      cfg.gridDim = dim3((unsigned)(sm_count / cluster * cluster));
       cfg.blockDim = dim3(TC_THREADS);
       cfg.dynamicSmemBytes = smem;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int n = 0;
       RQB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      max4 = n > 0 ? n : 1;
+      max_cl[cluster] = n > 0 ? n : 1;
     }
-    const int units = (ntiles64 + 3) / 4;
-    const int ncl = units < max4 ? units : max4;
-    return trace ? tc64_launch<true, 4>(p, 4 * ncl, smem, st) : tc64_launch<false, 4>(p, 4 * ncl, smem, st);
+    const int units = (ntiles64 + cluster - 1) / cluster;
+    const int ncl = units < max_cl[cluster] ? units : max_cl[cluster];
+    if (cluster == 4) return trace ? tc64_launch<true, 4>(p, 4 * ncl, smem, st) : tc64_launch<false, 4>(p, 4 * ncl, smem, st);
+    return trace ? tc64_launch<true, 8>(p, 8 * ncl, smem, st) : tc64_launch<false, 8>(p, 8 * ncl, smem, st);
   }
   const int units = (ntiles64 + 1) / 2;
   const int nclusters = units < sm_count / 2 ? units : sm_count / 2;

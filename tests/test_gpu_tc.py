@@ -161,7 +161,7 @@ def test_cta_pair_variant_returns_the_same_ids(tmp_path):
 @pytest.mark.skipif(__import__("os").environ.get("RQB200_TEST_UNVALIDATED", "0") != "1",
                     reason="rq_tc64_kernel (RQB200_TC_64=1) was written without GPU access at the end of round 1 and has not run "
                            "on hardware yet: bring it up with tools/pair64_probe.cu first, then set RQB200_TEST_UNVALIDATED=1")
-@pytest.mark.parametrize("cluster", ["1", "4"])
+@pytest.mark.parametrize("cluster", ["1", "4", "8"])
 def test_tc64_variant_returns_the_same_ids(tmp_path, cluster):
     """The opt-in 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M=128 CTA-pair MMAs, x staged by tensor-map TMA) must return
     exactly the ids of the default kernel: odd 64-row tile counts (the pair's second CTA past the end), a partial last
@@ -183,7 +183,7 @@ def test_tc64_variant_returns_the_same_ids(tmp_path, cluster):
         f"    np.save({str(tmp_path)!r} + f'/tc64_{{B}}_{{D}}_{{L}}.npy', ids.cpu().numpy())\n"
         "print('TC64 DONE')\n"
     )
-    env = dict(os.environ, RQB200_TC_64=cluster)      # "1": one CTA pair per cluster; "4": two pairs sharing B by TMA multicast
+    env = dict(os.environ, RQB200_TC_64=cluster)      # "1": one CTA pair per cluster; "4" / "8": two / four pairs sharing B by TMA multicast
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "TC64 DONE" in res.stdout, res.stdout + res.stderr
     assert os.environ.get("RQB200_TC_64", "0") != "1", "run this test with the default kernel in the parent process"

@@ -2,7 +2,7 @@
 # ncu captures of the tokeniser kernels through the Python-free harness (tools/tc_native_check.cu): one `--set full` capture
 # per variant plus the memory-system counters that decide the round-2 question "is the kernel bound by L2 -> SM bytes?"
 # (DESIGN.md 5.2b budget: codebook stream + x + Gram gathers against the L2 throughput cap).
-#   usage (GPU box, repo root):  bash tools/ncu_tc.sh [variant ...]     variant = default | pair | 64 | 64x4
+#   usage (GPU box, repo root):  bash tools/ncu_tc.sh [variant ...]     variant = default | pair | 64 | 64x4 | 64x8
 # Outputs gpurun_out/ncu_tc_<variant>.ncu-rep and a CSV of the counters below; read them in the build container with
 #   ncu -i gpurun_out/ncu_tc_<variant>.ncu-rep --page raw --csv
 set -u
@@ -15,6 +15,7 @@ for v in "${@:-default 64}"; do
       pair)    envs="RQB200_TC_PAIR=1" ; pat="rq_tc_kernel" ;;
       64)      envs="RQB200_TC_64=1" ; pat="rq_tc64_kernel" ;;
       64x4)    envs="RQB200_TC_64=4" ; pat="rq_tc64_kernel" ;;
+      64x8)    envs="RQB200_TC_64=8" ; pat="rq_tc64_kernel" ;;
       *) echo "unknown variant $variant"; continue ;;
     esac
     env $envs timeout 300 ncu --metrics $METRICS --clock-control none -k regex:$pat -s 2 -c 1 --csv \

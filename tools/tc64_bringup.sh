@@ -11,6 +11,8 @@ mkdir -p gpurun_out
     cmp /tmp/a_$1.ids /tmp/b_$1.ids && echo "IDS_IDENTICAL B=$1 (clusters of 2)"
     RQB200_TC_64=4 timeout 40 tools/bin/tc_native_check $1 $2 $3 $4 /tmp/c_$1.ids; echo "exit $?"
     cmp /tmp/a_$1.ids /tmp/c_$1.ids && echo "IDS_IDENTICAL B=$1 (clusters of 4, multicast)"
+    RQB200_TC_64=8 timeout 40 tools/bin/tc_native_check $1 $2 $3 $4 /tmp/d_$1.ids; echo "exit $?"
+    cmp /tmp/a_$1.ids /tmp/d_$1.ids && echo "IDS_IDENTICAL B=$1 (clusters of 8, multicast)"
   done
 } > gpurun_out/tc64_bringup.txt 2>&1
 cat gpurun_out/tc64_bringup.txt
