@@ -175,6 +175,7 @@ struct TcSmemMisc {
   uint32_t pad;
   uint32_t rowinfo[TC_BM];        // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
   TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
+  uint64_t xs_full, xs_free;      // kTma only: fp32 staging of x landed in the A slots / read out by every converter thread
 };
 
 
@@ -186,7 +187,15 @@ struct TcSmemMisc {
 // streams only ITS half of every codebook block (half the L2 and shared-memory traffic per row, and the same 2 x 16 KB ring
 // now covers twice the tensor time).  Barriers the leader waits on (a_full, b_full, t_empty) collect arrivals from both CTAs;
 // barriers the leader signals (a_empty, b_empty, t_full) are multicast commits.
-template <bool kTrace, bool kVec, bool kPair>
+// kTma = true (RQB200_TC_TMA=1, opt-in, NOT yet run on hardware): x reaches the converter through TMA instead of the LSU path,
+// staged IN PLACE in the A slots the chunk is about to occupy -- there is no other shared memory left in this kernel.  The
+// fp32 source of chunk kc is two 16 KB boxes (128 rows x 32 floats): box 0 lands in slot kc, box 1 in slot kc + 1 (the next
+// chunk's slot, already released by the previous tile); the converters pull both into registers, meet at a named barrier,
+// and only then write the fp16 image into slot kc, while warp 2 already fetches the next chunk into slots kc + 1 / kc + 2.
+// The last chunk has no next slot: its two boxes go through its own slot one after the other.  One chunk (32 KB) is in
+// flight at a time, but as bulk copies: no L1TEX miss tracking, no LSU queue shared with the epilogue's gathers (the measured
+// limit of the register path is 5-6 B/clk/SM at a ~6 K-cycle loaded latency).
+template <bool kTrace, bool kVec, bool kPair, bool kTma = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
@@ -216,6 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
       mbar_init(&ms->t_empty[i], kPair ? 2 * TC_NEPI_WARPS : TC_NEPI_WARPS * 32);
     }
     mbar_init(&ms->rowinfo_free, 128);   // the half-0 epilogue thread of every row
+    if (kTma) { mbar_init(&ms->xs_full, 1); mbar_init(&ms->xs_free, 1); }
     fence_mbar_init();
   }
   if (warp == 1) { if (kPair) tc_alloc2(&ms->tmem_base, 512); else tc_alloc(&ms->tmem_base, 512); }
@@ -352,6 +362,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
         tc_trace_add(p.stats, 0, w_te); tc_trace_add(p.stats, 1, w_af); tc_trace_add(p.stats, 2, w_bf);
         tc_trace_add(p.stats, 3, clock64() - tm_start); tc_trace_add(p.stats, 12, 1);
       }
+    } else if (kTma && warp == 2) {
+      // x producer of the in-place TMA path: one load step = the fp32 boxes of one chunk (two boxes, or one at a time for the
+      // last chunk of a tile).  A step may start when (a) the slots it lands in were released by the previous tile's last
+      // level and (b) every converter thread has read the previous step's boxes out (its box 1 sat in this step's slot).
+      uint32_t ls = 0, it = 0;
+      for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+        const int tile = min(TC_TILE_OF(unit), p.ntiles - 1);   // a pair's second CTA past the last tile loads that tile again (unused)
+        const int row0 = tile * TC_BM;                           // rows past B read as zero (tensor-map bounds)
+        for (int kc = 0; kc < nkc; ++kc) {
+          const bool last_chunk = (kc == nkc - 1);
+          mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 13);
+          if (!last_chunk) mbar_wait_guarded(&ms->a_empty[kc + 1], (it & 1) ^ 1, 13);
+          mbar_wait_guarded(&ms->xs_free, (ls & 1) ^ 1, 14);
+          if (tc_elect_one()) {
+            mbar_expect_tx(&ms->xs_full, last_chunk ? TC_ACHUNK_BYTES : 2 * TC_ACHUNK_BYTES);
+            tc_tma2d(sA + kc * TC_ACHUNK_BYTES, &p.tmapXh, kc * TC_KC, row0, &ms->xs_full);
+            if (!last_chunk) tc_tma2d(sA + (kc + 1) * TC_ACHUNK_BYTES, &p.tmapXh, kc * TC_KC + 32, row0, &ms->xs_full);
+          }
+          __syncwarp();
+          ++ls;
+          if (last_chunk) {
+            mbar_wait_guarded(&ms->xs_free, (ls & 1) ^ 1, 14);
+            if (tc_elect_one()) {
+              mbar_expect_tx(&ms->xs_full, TC_ACHUNK_BYTES);
+              tc_tma2d(sA + kc * TC_ACHUNK_BYTES, &p.tmapXh, kc * TC_KC + 32, row0, &ms->xs_full);
+            }
+            __syncwarp();
+            ++ls;
+          }
+        }
+      }
     }
   } else if (warp < 4 + TC_NCONV_WARPS) {
     // ============================================================== warpgroup 1: x fp32 -> fp16 swizzled A chunks
@@ -363,6 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
     const int cw = warp - 4;
     const int rsub = lane >> 3, q8 = lane & 7;
     uint32_t it = 0;
+    [[maybe_unused]] uint32_t ls = 0;     // kTma: load steps consumed (phase of xs_full)
     long long c_wait = 0, c_work = 0, c_ldwait = 0, c_cvt = 0;
     TC_EV_DECL();
     TC_T0(tcv);
@@ -412,6 +454,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
                        "r"(*reinterpret_cast<const uint32_t*>(&h1)) : "memory");
         }
       };
+      if constexpr (kTma) {
+        // in-place TMA path (see the kernel's header comment): box 0 of chunk kc sits in slot kc, box 1 in slot kc + 1 (or, for
+        // the last chunk, follows box 0 through slot kc).  Same lane -> (row, float4 column) mapping as the register path, so
+        // convert_half is shared: LDS.128 of a warp covers four whole 128-byte staging rows (conflict-free).
+        auto lds_half = [&](float4 (&v)[8], int slot) {
+          const unsigned char* sp = sA + slot * TC_ACHUNK_BYTES + srow + q8 * 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(sp + i * 512);
+        };
+#pragma unroll 1
+        for (int kc = 0; kc < nkc; ++kc) {
+          const bool last_chunk = (kc == nkc - 1);
+          mbar_wait_guarded(&ms->xs_full, ls & 1, 12);
+          if (cw == 0) TC_EV(1, 1, it * 16 + kc);
+          lds_half(va, kc);
+          if (!last_chunk) lds_half(vb, kc + 1);
+          tc_conv_sync();                       // every converter thread holds its staging bytes: the slots may be overwritten
+          if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
+          ++ls;
+          if (last_chunk) {
+            mbar_wait_guarded(&ms->xs_full, ls & 1, 12);
+            lds_half(vb, kc);
+            tc_conv_sync();
+            if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
+            ++ls;
+          }
+          convert_half(va, 2 * kc);
+          convert_half(vb, 2 * kc + 1);
+          if (last_chunk) {
+            mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+              for (int o = 4; o > 0; o >>= 1) {      // the 8 lanes (q8) that share row 4r + rsub
+                sm[r] = fmaxf(sm[r], __shfl_xor_sync(0xffffffffu, sm[r], o));
+                s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+              }
+              if (q8 == 0) ms->rowinfo[cw * 32 + rsub + 4 * r] = (tc_bf16_up(sm[r]) << 16) | tc_bf16_up(s2[r]);
+            }
+          }
+          fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+          if constexpr (kPair) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->a_full[kc]), 0));
+          } else {
+            mbar_arrive(&ms->a_full[kc]);
+          }
+          if (cw == 0) TC_EV(1, 2, it * 16 + kc);
+        }
+        continue;                              // next tile
+      }
       // chunks are produced in the order the MMA issuer consumes them: step i -> chunk tc_rot(i)
       load_half(va, 2 * rot0);
       load_half(vb, 2 * rot0 + 1);
@@ -787,9 +880,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
   }
 }
 
-template <bool kTrace, bool kVec, bool kPair>
+template <bool kTrace, bool kVec, bool kPair, bool kTma = false>
 static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = rq_tc_kernel<kTrace, kVec, kPair>;
+  auto kern = rq_tc_kernel<kTrace, kVec, kPair, kTma>;
   RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (kPair) {
     cudaLaunchConfig_t cfg{};
@@ -811,7 +904,8 @@ static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) 
 }
 
 template <bool kPair>
-static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, bool vec_ok) {
+static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, bool vec_ok, bool tma) {
+  if (tma && vec_ok) return trace ? tc_launch<true, true, kPair, true>(p, grid, smem, st) : tc_launch<false, true, kPair, true>(p, grid, smem, st);
   if (trace) return vec_ok ? tc_launch<true, true, kPair>(p, grid, smem, st) : tc_launch<true, false, kPair>(p, grid, smem, st);
   return vec_ok ? tc_launch<false, true, kPair>(p, grid, smem, st) : tc_launch<false, false, kPair>(p, grid, smem, st);
 }
@@ -856,6 +950,14 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   // RQB200_TC_64=1: clusters of 2 (one pair); =4 / =8: clusters of 4 / 8 (two / four pairs sharing the codebook blocks by TMA multicast)
   static const int opt_64 = []() { const char* e = getenv("RQB200_TC_64"); return (e && e[0] == '1') ? 2 : (e && e[0] == '4') ? 4 : (e && e[0] == '8') ? 8 : 0; }();
   if (opt_64 && vec_ok && sm_count >= opt_64) return tc64_run(p, sm_count, trace, opt_64, st);
+  // in-place TMA staging of x (kTma instantiation of rq_tc_kernel, single-CTA or pair): opt-in, not yet run on hardware
+  static const int opt_tma = []() { const char* e = getenv("RQB200_TC_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  const bool tma = opt_tma && vec_ok;
+  if (tma) {
+    p.rot = 0;                                  // the in-place scheme walks the chunks in slot order
+    int rc = tc_encode_2d(&p.tmapXh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.x, (uint64_t)D, (uint64_t)B, (uint64_t)ldx * 4, 32, TC_BM);
+    if (rc) return rc;
+  }
   // CTA-pair variant (cta_group::2): opt-in while it is being brought up
   static const int opt_pair = []() { const char* e = getenv("RQB200_TC_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
   if (opt_pair && p.ntiles >= 2 && sm_count >= 2) {
@@ -863,8 +965,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
     if (rc) return rc;
     const int npairs = (p.ntiles + 1) / 2;
     const int nclusters = npairs < sm_count / 2 ? npairs : sm_count / 2;
-    return tc_dispatch<true>(p, 2 * nclusters, smem, st, trace, vec_ok);
+    return tc_dispatch<true>(p, 2 * nclusters, smem, st, trace, vec_ok, tma);
   }
   const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-  return tc_dispatch<false>(p, grid, smem, st, trace, vec_ok);
+  return tc_dispatch<false>(p, grid, smem, st, trace, vec_ok, tma);
 }

@@ -52,13 +52,7 @@ struct Tc64Misc {
   uint32_t mask[TC64_BM][8];      // candidate bitmask of the `many` rows (each warp writes the 2 words of its 64 columns)
 };
 
-__device__ __forceinline__ void tc64_tma2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// same, delivered to the same shared-memory offset (data and mbarrier) of every CTA whose bit is set in `mask`
+// tc_tma2d (tc_common.cuh) delivered to the same shared-memory offset (data and mbarrier) of every CTA whose bit is set in `mask`
 __device__ __forceinline__ void tc64_tma2d_mc(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint16_t mask) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
@@ -197,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           mbar_wait_guarded(&ms->x_empty[st], (u & 1) ^ 1, 8);
           if (tc_elect_one()) {
             mbar_expect_tx(&ms->x_full[st], TC64_XSTAGE_BYTES);
-            tc64_tma2d(sX + st * TC64_XSTAGE_BYTES, &p.tmapX, kc * TC_KC, tile * TC64_BM, &ms->x_full[st]);
+            tc_tma2d(sX + st * TC64_XSTAGE_BYTES, &p.tmapX, kc * TC_KC, tile * TC64_BM, &ms->x_full[st]);
           }
           __syncwarp();
         }

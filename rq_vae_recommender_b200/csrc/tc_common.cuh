@@ -105,6 +105,16 @@ __device__ __forceinline__ void tc_tma2d_pair(void* smem_dst, const CUtensorMap*
       : "memory");
 }
 
+// one box of a 2-D tensor map -> this CTA's shared memory, bytes counted on a local mbarrier
+__device__ __forceinline__ void tc_tma2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// named barrier 1: the four converter warps (128 threads)
+__device__ __forceinline__ void tc_conv_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -180,6 +190,7 @@ struct TcParams {
   int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
   int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
   CUtensorMap tmapX;    // rq_tc64_kernel only: x as a [B][D] fp32 tensor, box = 64 rows x 64 floats (one 16 KB staging stage)
+  CUtensorMap tmapXh;   // rq_tc_kernel<.., kTma>: x as a [B][D] fp32 tensor, box = 128 rows x 32 floats (half a chunk, one A slot)
   CUtensorMap tmapB2;   // rq_tc64_kernel, clusters of 4: the codebook blob with a 64-row box (8 KB multicast slices)
 };
 

@@ -157,15 +157,23 @@ def test_cta_pair_variant_returns_the_same_ids(tmp_path):
         assert np.array_equal(ids, pair), (B, D, L, int((ids != pair).any(axis=1).sum()))
 
 
+UNVALIDATED = {                      # kernel variants written without GPU access at the end of round 1
+    "tc64": {"RQB200_TC_64": "1"},            # 64 rows per CTA, M=128 pair MMAs, x staged by TMA; clusters of 2
+    "tc64x4": {"RQB200_TC_64": "4"},          # ... clusters of 4: two pairs share the codebook blocks by TMA multicast
+    "tc64x8": {"RQB200_TC_64": "8"},          # ... clusters of 8
+    "tma": {"RQB200_TC_TMA": "1"},            # 128-row kernel, x through in-place TMA staging in the A slots
+    "tma_pair": {"RQB200_TC_TMA": "1", "RQB200_TC_PAIR": "1"},
+}
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(__import__("os").environ.get("RQB200_TEST_UNVALIDATED", "0") != "1",
-                    reason="rq_tc64_kernel (RQB200_TC_64=1) was written without GPU access at the end of round 1 and has not run "
-                           "on hardware yet: bring it up with tools/pair64_probe.cu first, then set RQB200_TEST_UNVALIDATED=1")
-@pytest.mark.parametrize("cluster", ["1", "4", "8"])
-def test_tc64_variant_returns_the_same_ids(tmp_path, cluster):
-    """The opt-in 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M=128 CTA-pair MMAs, x staged by tensor-map TMA) must return
-    exactly the ids of the default kernel: odd 64-row tile counts (the pair's second CTA past the end), a partial last
-    tile (TMA zero fill), strided rows, and inputs that force the `many` path (exact duplicates among the codes)."""
+                    reason="these kernel variants were written without GPU access at the end of round 1 and have not run on "
+                           "hardware yet: bring them up with tools/tc64_bringup.sh first, then set RQB200_TEST_UNVALIDATED=1")
+@pytest.mark.parametrize("variant", sorted(UNVALIDATED))
+def test_unvalidated_variants_return_the_same_ids(tmp_path, variant):
+    """Every opt-in variant must return exactly the ids of the default kernel: odd tile counts (a pair's second CTA past the
+    end), a partial last tile (TMA zero fill), inputs that force the `many` path (exact duplicates among the codes), L = 8."""
     import os, subprocess, sys
     from rq_vae_recommender_b200 import ops
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -180,18 +188,18 @@ def test_tc64_variant_returns_the_same_ids(tmp_path, cluster):
         "    if B == 513:\n"
         "        cbs[0][200] = cbs[0][17]; cbs[0][90] = cbs[0][17]; x[:64] = cbs[0][17] + 1e-4 * x[:64]\n"
         "    ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs])\n"
-        f"    np.save({str(tmp_path)!r} + f'/tc64_{{B}}_{{D}}_{{L}}.npy', ids.cpu().numpy())\n"
-        "print('TC64 DONE')\n"
+        f"    np.save({str(tmp_path)!r} + f'/v_{{B}}_{{D}}_{{L}}.npy', ids.cpu().numpy())\n"
+        "print('VARIANT DONE')\n"
     )
-    env = dict(os.environ, RQB200_TC_64=cluster)      # "1": one CTA pair per cluster; "4" / "8": two / four pairs sharing B by TMA multicast
+    env = dict(os.environ, **UNVALIDATED[variant])
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0 and "TC64 DONE" in res.stdout, res.stdout + res.stderr
-    assert os.environ.get("RQB200_TC_64", "0") != "1", "run this test with the default kernel in the parent process"
+    assert res.returncode == 0 and "VARIANT DONE" in res.stdout, res.stdout + res.stderr
+    assert not any(os.environ.get(k, "0") != "0" for k in UNVALIDATED[variant]), "run the parent process with the default kernel"
     for (B, D, L) in shapes:
         x, cbs = I.rq_problem(max(B, 1024), D, 256, L, seed=B + D)
         x = x[:B]
         if B == 513:
             cbs[0][200] = cbs[0][17]; cbs[0][90] = cbs[0][17]; x[:64] = cbs[0][17] + 1e-4 * x[:64]
         ids = ops.rq_tokenize_tc(torch.from_numpy(x).cuda(), [torch.from_numpy(c).cuda() for c in cbs]).cpu().numpy()
-        got = np.load(tmp_path / f"tc64_{B}_{D}_{L}.npy")
-        assert np.array_equal(ids, got), (B, D, L, int((ids != got).any(axis=1).sum()))
+        got = np.load(tmp_path / f"v_{B}_{D}_{L}.npy")
+        assert np.array_equal(ids, got), (variant, B, D, L, int((ids != got).any(axis=1).sum()))
