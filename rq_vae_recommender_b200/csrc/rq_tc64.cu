@@ -358,11 +358,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           if (p.one) {   // opaque always-true branch = basic-block boundary (see rq_tc.cu: keeps the prefetches early in SASS)
             float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+            for (int v = 0; v < 4; ++v) {      // two scores per insertion: 8 min/max instead of 10 (tc_select.cuh)
+              tcs_key_insert2(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0,
+                              fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
+              tcs_key_insert2(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2,
+                              fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
             }
             tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
           }

@@ -60,6 +60,18 @@ TCS_HD void tcs_key_insert(float a, uint32_t e, float& q1, float& q2, float& q3)
   q1 = fminf(q1, key);
 }
 
+// stage 1, two scores per call: 8 min/max instructions instead of 10 (sm_100 has three-input FMNMX3, which ptxas forms from
+// the nested fminf).  With lo <= hi the two keys and q1 <= q2 <= q3 the running triple, the k-th smallest of the merged
+// lists is min over i + j = k of max(q_i, key_j):  r1 = min(q1, lo),  r2 = min(max(q1, lo), q2, hi),
+// r3 = min(q3, max(q2, lo), max(q1, hi)).
+TCS_HD void tcs_key_insert2(float a, uint32_t ea, float b, uint32_t eb, float& q1, float& q2, float& q3) {
+  const float ka = tcs_u2f((tcs_f2u(a) & TCS_KEY_MASK) | ea), kb = tcs_u2f((tcs_f2u(b) & TCS_KEY_MASK) | eb);
+  const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
+  q3 = fminf(fminf(q3, fmaxf(q2, lo)), fmaxf(q1, hi));
+  q2 = fminf(fminf(fmaxf(q1, lo), q2), hi);
+  q1 = fminf(q1, lo);
+}
+
 // stage 2: merge the key triple of the chunk whose first column is `cbase` into the running top-3
 TCS_HD void tcs_merge(float q1, float q2, float q3, int cbase, float& m1, float& m2, float& m3, int& i1, int& i2) {
   tc_insert(q1, cbase + (int)(tcs_f2u(q1) & TCS_IDX_MASK), m1, m2, m3, i1, i2);

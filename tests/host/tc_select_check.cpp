@@ -9,7 +9,30 @@
 
 struct Result { float m1, m2, m3; int i1, i2; };
 
-// mirrors the kernel: two warps scan 128 columns each in 16-column chunks, then the halves are merged (rq_tc.cu)
+// mode 1 mirrors rq_tc64_kernel: four warps scan 64 columns each, two scores per insertion (tcs_key_insert2), then the
+// three partner triples are merged into the owner's
+static Result scan_row64(const float* a) {
+  Result h[4];
+  for (int part = 0; part < 4; ++part) {
+    float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY; int i1 = 0, i2 = 0;
+    for (int c = 0; c < 64; c += TCS_CHUNK) {
+      float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
+      for (int e = 0; e < TCS_CHUNK; e += 2)
+        tcs_key_insert2(a[part * 64 + c + e], (uint32_t)e, a[part * 64 + c + e + 1], (uint32_t)(e + 1), q1, q2, q3);
+      tcs_merge(q1, q2, q3, part * 64 + c, m1, m2, m3, i1, i2);
+    }
+    h[part] = Result{m1, m2, m3, i1, i2};
+  }
+  Result r = h[0];
+  for (int part = 1; part < 4; ++part) {
+    tc_insert(h[part].m1, h[part].i1, r.m1, r.m2, r.m3, r.i1, r.i2);
+    tc_insert(h[part].m2, h[part].i2, r.m1, r.m2, r.m3, r.i1, r.i2);
+    r.m3 = fminf(r.m3, fmaxf(r.m2, h[part].m3));
+  }
+  return r;
+}
+
+// mode 0 mirrors rq_tc_kernel: two warps scan 128 columns each in 16-column chunks, then the halves are merged (rq_tc.cu)
 static Result scan_row(const float* a) {
   Result h[2];
   for (int half = 0; half < 2; ++half) {
@@ -30,6 +53,7 @@ static Result scan_row(const float* a) {
 
 int main(int argc, char** argv) {
   const int trials = argc > 1 ? atoi(argv[1]) : 200000;
+  const int mode = argc > 2 ? atoi(argv[2]) : 0;
   std::mt19937 rng(1234);
   std::normal_distribution<float> nd(0.f, 1.f);
   std::uniform_real_distribution<float> ud(0.f, 1.f);
@@ -55,7 +79,7 @@ int main(int argc, char** argv) {
       if (rng() & 1) a[rng() % 256] = a[kmin];
       if (rng() & 1) margin = 0.f;
     }
-    const Result r = scan_row(a.data());
+    const Result r = mode ? scan_row64(a.data()) : scan_row(a.data());
     const float thr = tcs_threshold(r.m1, margin);
     const bool flagged = !(r.m2 > thr), many = flagged && !(r.m3 > thr);
     // brute force

@@ -20,6 +20,7 @@ def test_packed_key_selection_never_loses_a_candidate(tmp_path):
     exe = tmp_path / "tc_select_check"
     src = os.path.join(ROOT, "tests", "host", "tc_select_check.cpp")
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), src], check=True)
-    res = subprocess.run([str(exe), "200000"], capture_output=True, text=True)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert " bad 0 " in res.stdout, res.stdout
+    for mode in ("0", "1"):      # 0: rq_tc_kernel's scan (2 x 128 columns); 1: rq_tc64_kernel's (4 x 64 columns, two scores per insertion)
+        res = subprocess.run([str(exe), "200000", mode], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert " bad 0 " in res.stdout, res.stdout
