@@ -463,6 +463,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(sp + i * 512);
         };
+        // convert_half split in two: statistics + fp16 packing BEFORE the converters' barrier, the stores after it.  The
+        // packing consumes the loaded registers, so every LDS has returned its data before the barrier is signalled: the
+        // barrier alone only orders the ISSUE of the loads, and the bulk copy that refills the slot does not pass through
+        // the LSU queue they may still be waiting in (first hardware run: the un-split version returned a few wrong ids).
+        auto pack_half = [&](const float4 (&v)[8], uint2 (&hp)[8]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = v[i];
+            s2[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, s2[i]))));
+            sm[i] = fmaxf(fmaxf(sm[i], fmaxf(fabsf(a.x), fabsf(a.y))), fmaxf(fabsf(a.z), fabsf(a.w)));
+            const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+            hp[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          }
+        };
+        auto store_half = [&](const uint2 (&hp)[8], int h) {     // same addresses as convert_half
+          const uint32_t f = q8 + 8 * (h & 1);
+          const uint32_t base_e = smem_u32(sA) + (h >> 1) * TC_ACHUNK_BYTES + srow + (((f >> 1) ^ (uint32_t)rsub) << 4) + (f & 1) * 8;
+          const uint32_t base_o = base_e ^ (4u << 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t addr = ((i & 1) ? base_o : base_e) + i * 512;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(hp[i].x), "r"(hp[i].y) : "memory");
+          }
+        };
+        uint2 pa[8], pb[8];
 #pragma unroll 1
         for (int kc = 0; kc < nkc; ++kc) {
           const bool last_chunk = (kc == nkc - 1);
@@ -470,18 +495,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
           if (cw == 0) TC_EV(1, 1, it * 16 + kc);
           lds_half(va, kc);
           if (!last_chunk) lds_half(vb, kc + 1);
-          tc_conv_sync();                       // every converter thread holds its staging bytes: the slots may be overwritten
+          pack_half(va, pa);
+          if (!last_chunk) pack_half(vb, pb);
+          tc_conv_sync();                       // every converter thread HOLDS its staging bytes: the slots may be overwritten
           if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
           ++ls;
           if (last_chunk) {
             mbar_wait_guarded(&ms->xs_full, ls & 1, 12);
             lds_half(vb, kc);
+            pack_half(vb, pb);
             tc_conv_sync();
             if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
             ++ls;
           }
-          convert_half(va, 2 * kc);
-          convert_half(vb, 2 * kc + 1);
+          store_half(pa, 2 * kc);
+          store_half(pb, 2 * kc + 1);
           if (last_chunk) {
             mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
 #pragma unroll
