@@ -90,5 +90,40 @@ int main(int argc, char** argv) {
   printf("B=%d D=%d L=%d TC_64=%s TC_PAIR=%s TC_TMA=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
          B, D, L, v64 ? v64 : "-", vp ? vp : "-", vt ? vt : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
          B / (ms / iters) * 1e-3);
+  // RQB200_TC_TRACE=1: one more run with the event timeline of CTA 0 switched on (stats[3] = stats[4] = 1, >= 4096 ints; the
+  // records are (tag << 56 | payload << 48 | clock) at ((long long*)(stats + 128))[role * 256 ...], see TC_EV in tc_common.cuh)
+  const char* vtr = getenv("RQB200_TC_TRACE");
+  if (vtr && vtr[0] == '1') {
+    int* dtr; CK(cudaMalloc(&dtr, 4096 * 4)); CK(cudaMemset(dtr, 0, 4096 * 4));
+    const int on[2] = {1, 1};
+    CK(cudaMemcpy(dtr + 3, on, 8, cudaMemcpyHostToDevice));
+    if (run(dx, D, B, dstate, D, K, L, dids, dtr, nullptr)) { printf("traced run failed: %s\n", last_error()); return 1; }
+    CK(cudaDeviceSynchronize());
+    std::vector<int> tr(4096);
+    CK(cudaMemcpy(tr.data(), dtr, 4096 * 4, cudaMemcpyDeviceToHost));
+    const long long* ev = reinterpret_cast<const long long*>(tr.data() + 128);
+    struct Rec { long long clk; int role, tag, pay; };
+    std::vector<Rec> recs;
+    for (int r = 0; r < 4; ++r)
+      for (int i = 0; i < 256; ++i) {
+        const long long e = ev[r * 256 + i];
+        if (e) recs.push_back(Rec{e & 0xffffffffffffLL, r, (int)((e >> 56) & 0xff), (int)((e >> 48) & 0xff)});
+      }
+    for (size_t i = 1; i < recs.size(); ++i)      // insertion sort by clock (a few hundred records)
+      for (size_t j = i; j > 0 && recs[j].clk < recs[j - 1].clk; --j) { Rec t = recs[j]; recs[j] = recs[j - 1]; recs[j - 1] = t; }
+    static const char* role_name[4] = {"MMA ", "CONV", "EPI0", "EPI1"};
+    static const char* tag_name[4][6] = {
+        {"", "level start (t_empty ok)", "a_full ok, chunk step", "level issued", "", ""},
+        {"", "a_empty/x_full ok, chunk step", "chunk converted+arrived", "", "", ""},
+        {"", "t_full ok", "scan end", "merged / verdict out", "tmem released", "level done (re-rank, id out)"},
+        {"", "t_full ok", "scan end", "id received", "", ""}};
+    printf("timeline of CTA 0 (cycles since first event; payload = tile_index*16 + level-or-step), %zu events\n", recs.size());
+    for (const Rec& q : recs) {
+      const bool step = (q.role == 0 && q.tag == 2) || q.role == 1;
+      if (step && (q.pay & 15) != 0 && (q.pay & 15) != (D / 64 - 1)) continue;      // chunk steps: first and last only
+      printf("%9lld  %*s%s %-32s tile %d %s %d\n", q.clk - recs[0].clk, 4 * q.role, "", role_name[q.role],
+             q.tag < 6 ? tag_name[q.role][q.tag] : "?", q.pay >> 4, step ? "step" : "lvl", q.pay & 15);
+    }
+  }
   return bad ? 1 : 0;
 }
