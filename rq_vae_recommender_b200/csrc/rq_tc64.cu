@@ -27,19 +27,16 @@
 #define TC64_BM 64                                  // rows per CTA
 #define TC64_ACHUNK_BYTES (TC64_BM * TC_KC * 2)     // 8 KB
 #define TC64_XSTAGE_BYTES (TC64_BM * TC_KC * 4)     // 16 KB: 64 rows x 64 fp32
-#ifndef TC64_NB
-#define TC64_NB 4
-#endif
-#ifndef TC64_NX
-#define TC64_NX 3
-#endif
+#define TC64_NB 4                                   // default depth of the codebook ring   (run time: RQB200_TC64_NB, p.nb)
+#define TC64_NX 3                                   // default depth of the x staging ring  (run time: RQB200_TC64_NX, p.nx)
+#define TC64_MAXS 6                                 // barrier slots per ring; nb + nx <= 7 stages of 16 KB fit beside A
 #define TC64_NBUF 4                                 // accumulator buffers of 128 TMEM columns
 
 struct Tc64Misc {
   uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
-  uint64_t b_full[TC64_NB], b_empty[TC64_NB];
-  uint64_t b_peer[TC64_NB];       // kCl = 4 only, pair leader: the peer CTA's codebook stage has landed (forwarded)
-  uint64_t x_full[TC64_NX], x_empty[TC64_NX];
+  uint64_t b_full[TC64_MAXS], b_empty[TC64_MAXS];
+  uint64_t b_peer[TC64_MAXS];      // kCl = 4 only, pair leader: the peer CTA's codebook stage has landed (forwarded)
+  uint64_t x_full[TC64_MAXS], x_empty[TC64_MAXS];
   uint64_t t_full[TC64_NBUF], t_empty[TC64_NBUF];
   uint64_t rowinfo_free;
   uint32_t tmem_base;
@@ -65,6 +62,12 @@ __device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // named barriers of one row group (4 warps = 128 threads)
+// position in a ring of n stages: stage index + phase parity, advanced without divisions (n is a run-time parameter)
+struct Tc64Ring {
+  uint32_t st, ph, n;
+  __device__ __forceinline__ explicit Tc64Ring(int n_) : st(0), ph(0), n((uint32_t)n_) {}
+  __device__ __forceinline__ void next() { if (++st == n) { st = 0; ph ^= 1u; } }
+};
 __device__ __forceinline__ void tc64_grp_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc64_grp_arrive(int id) {
   __threadfence_block();
@@ -78,9 +81,9 @@ template <bool kTrace, int kCl>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                             // [TC_MAX_KC][8 KB]
-  unsigned char* sB = sA + TC_MAX_KC * TC64_ACHUNK_BYTES;              // [TC64_NB][16 KB]
-  unsigned char* sX = sB + TC64_NB * TC_BSTAGE_BYTES;                  // [TC64_NX][16 KB]
-  Tc64Misc* ms = reinterpret_cast<Tc64Misc*>(sX + TC64_NX * TC64_XSTAGE_BYTES);
+  unsigned char* sB = sA + TC_MAX_KC * TC64_ACHUNK_BYTES;              // [p.nb][16 KB]
+  unsigned char* sX = sB + p.nb * TC_BSTAGE_BYTES;                     // [p.nx][16 KB]
+  Tc64Misc* ms = reinterpret_cast<Tc64Misc*>(sX + p.nx * TC64_XSTAGE_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
@@ -98,12 +101,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();  // the swizzle pattern needs a 1024-byte aligned base
     for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], 2 * TC_NCONV_WARPS); mbar_init(&ms->a_empty[i], 1); }
-    for (int i = 0; i < TC64_NB; ++i) {
+    for (int i = 0; i < TC64_MAXS; ++i) {
       mbar_init(&ms->b_full[i], 1);
       mbar_init(&ms->b_empty[i], kCl / 2);   // one multicast commit per pair leader that reads the (shared) stage
       mbar_init(&ms->b_peer[i], 1);
     }
-    for (int i = 0; i < TC64_NX; ++i) { mbar_init(&ms->x_full[i], 1); mbar_init(&ms->x_empty[i], TC_NCONV_WARPS); }
+    for (int i = 0; i < TC64_MAXS; ++i) { mbar_init(&ms->x_full[i], 1); mbar_init(&ms->x_empty[i], TC_NCONV_WARPS); }
     for (int i = 0; i < TC64_NBUF; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS); }
     mbar_init(&ms->rowinfo_free, TC64_BM);       // the owner thread of every row
     fence_mbar_init();
@@ -121,12 +124,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     if (warp == 0) {
       // this CTA's 128 codes (column half = crank) of every (level, k chunk) block; the bytes of both CTAs are counted on
       // the LEADER's b_full, which is what its MMA warp waits on
-      uint32_t s = 0;
+      Tc64Ring rb(p.nb);
       for (int unit = u_first; unit < u_count; unit += u_step)
         for (int l = 0; l < L; ++l)
-          for (int kc = 0; kc < nkc; ++kc, ++s) {
-            const uint32_t st = s % TC64_NB, u = s / TC64_NB;
-            mbar_wait_guarded(&ms->b_empty[st], (u & 1) ^ 1, 1);      // local: the leaders' commits are multicast
+          for (int kc = 0; kc < nkc; ++kc, rb.next()) {
+            const uint32_t st = rb.st;
+            mbar_wait_guarded(&ms->b_empty[st], rb.ph ^ 1u, 1);       // local: the leaders' commits are multicast
             if (tc_elect_one()) {
               const int blk_row = ((l * 2 + (int)crank) * nkc + kc) * 128;      // first blob row of this CTA's half-block
               if constexpr (kCl == 2) {
@@ -148,7 +151,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
       const uint32_t idesc = tc_idesc(128, 256);
       const uint16_t all_mask = (uint16_t)((1u << kCl) - 1u);
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      uint32_t s = 0, g = 0, it = 0;
+      uint32_t g = 0, it = 0;
+      Tc64Ring rb(p.nb);
       TC_EV_DECL();
       for (int unit = u_first; unit < u_count; unit += u_step, ++it)
         for (int l = 0; l < L; ++l, ++g) {
@@ -157,14 +161,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           TC_EV(0, 1, it * 16 + l);
           tc_fence_after();
           const uint32_t d_tmem = TC64_TMEM_BASE() + buf * 128;
-          for (int kc = 0; kc < nkc; ++kc, ++s) {
+          for (int kc = 0; kc < nkc; ++kc, rb.next()) {
             if (l == 0) {
               mbar_wait_guarded_cluster(&ms->a_full[kc], it & 1, 3);
               TC_EV(0, 2, it * 16 + kc);
             }
-            const uint32_t st = s % TC64_NB;
-            mbar_wait_guarded_cluster(&ms->b_full[st], (s / TC64_NB) & 1, 4);
-            if constexpr (kCl > 2) mbar_wait_guarded_cluster(&ms->b_peer[st], (s / TC64_NB) & 1, 10);
+            const uint32_t st = rb.st;
+            mbar_wait_guarded_cluster(&ms->b_full[st], rb.ph, 4);
+            if constexpr (kCl > 2) mbar_wait_guarded_cluster(&ms->b_peer[st], rb.ph, 10);
             tc_fence_after();
             const uint64_t adesc = tc_smem_desc(a_base + kc * TC64_ACHUNK_BYTES);
             const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
@@ -183,12 +187,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     } else if (warp == 2) {
       // x producer: one 64-row x 64-float box per k chunk.  Rows past B read as zero (tensor-map bounds); a pair's second
       // CTA past the last 64-row tile loads the last tile again (its scores are never stored).
-      uint32_t s = 0;
+      Tc64Ring rx(p.nx);
       for (int unit = u_first; unit < u_count; unit += u_step) {
         const int tile = min(kCl * unit + (int)rank, ntiles64 - 1);
-        for (int kc = 0; kc < nkc; ++kc, ++s) {
-          const uint32_t st = s % TC64_NX, u = s / TC64_NX;
-          mbar_wait_guarded(&ms->x_empty[st], (u & 1) ^ 1, 8);
+        for (int kc = 0; kc < nkc; ++kc, rx.next()) {
+          const uint32_t st = rx.st;
+          mbar_wait_guarded(&ms->x_empty[st], rx.ph ^ 1u, 8);
           if (tc_elect_one()) {
             mbar_expect_tx(&ms->x_full[st], TC64_XSTAGE_BYTES);
             tc_tma2d(sX + st * TC64_XSTAGE_BYTES, &p.tmapX, kc * TC_KC, tile * TC64_BM, &ms->x_full[st]);
@@ -199,11 +203,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     } else if (kCl > 2 && warp == 3 && crank == 1) {
       // the leader's MMA warp reads the codebook stage of BOTH CTAs of the pair; with multicast loads each CTA's bytes are
       // counted on its own b_full, so the peer forwards every completed phase to the leader
-      uint32_t s = 0;
+      Tc64Ring rb(p.nb);
       for (int unit = u_first; unit < u_count; unit += u_step)
-        for (int i = 0; i < L * nkc; ++i, ++s) {
-          const uint32_t st = s % TC64_NB;
-          mbar_wait_guarded(&ms->b_full[st], (s / TC64_NB) & 1, 11);
+        for (int i = 0; i < L * nkc; ++i, rb.next()) {
+          const uint32_t st = rb.st;
+          mbar_wait_guarded(&ms->b_full[st], rb.ph, 11);
           if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->b_peer[st]), leader));
           __syncwarp();
         }
@@ -214,7 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     // a warp reads 512 contiguous staging bytes (LDS.128, conflict-free) and writes two 128-byte A rows (STS.64).
     const int cw = warp - 4;
     const int hi = lane >> 4, q = lane & 15;
-    uint32_t it = 0, s = 0;
+    uint32_t it = 0;
+    Tc64Ring rx(p.nx);
     TC_EV_DECL();
 #pragma unroll 1
     for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
@@ -222,9 +227,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sm[j] = 0.f; s2[j] = 0.f; }
 #pragma unroll 1
-      for (int kc = 0; kc < nkc; ++kc, ++s) {
-        const uint32_t st = s % TC64_NX;
-        mbar_wait_guarded(&ms->x_full[st], (s / TC64_NX) & 1, 9);
+      for (int kc = 0; kc < nkc; ++kc, rx.next()) {
+        const uint32_t st = rx.st;
+        mbar_wait_guarded(&ms->x_full[st], rx.ph, 9);
         mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);     // the last level of the previous tile released this chunk
         if (cw == 0) TC_EV(1, 1, it * 16 + kc);
         const unsigned char* xs = sX + st * TC64_XSTAGE_BYTES;
@@ -583,8 +588,16 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
                     TC_KC, TC64_BM);
   if (rc) return rc;
   const int ntiles64 = (p.B + TC64_BM - 1) / TC64_BM;
-  const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)TC64_NB * TC_BSTAGE_BYTES +
-                      (size_t)TC64_NX * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
+  // ring depths: defaults, or RQB200_TC64_NB / RQB200_TC64_NX for same-box sweeps (nb + nx <= 7 stages fit beside A)
+  static const int env_nb = []() { const char* e = getenv("RQB200_TC64_NB"); return e ? atoi(e) : TC64_NB; }();
+  static const int env_nx = []() { const char* e = getenv("RQB200_TC64_NX"); return e ? atoi(e) : TC64_NX; }();
+  if (env_nb < 1 || env_nb > TC64_MAXS || env_nx < 1 || env_nx > TC64_MAXS || env_nb + env_nx > 7) {
+    rqb_set_error("tokenize_tc: RQB200_TC64_NB=%d / RQB200_TC64_NX=%d out of range (1..%d each, sum <= 7)", env_nb, env_nx, TC64_MAXS);
+    return RQB_ERR_INVALID;
+  }
+  p.nb = env_nb; p.nx = env_nx;
+  const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)p.nb * TC_BSTAGE_BYTES +
+                      (size_t)p.nx * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
   if ((cluster == 4 || cluster == 8) && ntiles64 > 2) {
     // how many clusters of this size (one CTA per SM at this shared-memory size) the device can hold at once: GPC boundaries
     // make this less than sm_count / cluster (queried, not assumed)

@@ -192,6 +192,7 @@ struct TcParams {
   CUtensorMap tmapX;    // rq_tc64_kernel only: x as a [B][D] fp32 tensor, box = 64 rows x 64 floats (one 16 KB staging stage)
   CUtensorMap tmapXh;   // rq_tc_kernel<.., kTma>: x as a [B][D] fp32 tensor, box = 128 rows x 32 floats (half a chunk, one A slot)
   CUtensorMap tmapB2;   // rq_tc64_kernel, clusters of 4: the codebook blob with a 64-row box (8 KB multicast slices)
+  int nb, nx;             // rq_tc64_kernel: depth of the codebook ring / the x staging ring (16 KB stages)
 };
 
 struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
