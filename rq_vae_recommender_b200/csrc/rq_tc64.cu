@@ -38,15 +38,16 @@ struct Tc64Misc {
   uint64_t b_peer[TC64_MAXS];      // kCl = 4 only, pair leader: the peer CTA's codebook stage has landed (forwarded)
   uint64_t x_full[TC64_MAXS], x_empty[TC64_MAXS];
   uint64_t t_full[TC64_NBUF], t_empty[TC64_NBUF];
-  uint64_t rowinfo_free;
+  // everything below exists once per epilogue GROUP (kGrp = 2: two groups of four warps work on alternate tiles)
+  uint64_t rowinfo_free[2];
   uint32_t tmem_base;
-  uint32_t many_word[2];          // per row group: ballot of the rows with >= 3 candidates at the level being merged
+  uint32_t many_word[2][2];       // per row group: ballot of the rows with >= 3 candidates at the level being merged
   uint32_t pad;
-  uint32_t rowinfo[TC64_BM];      // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
-  float thr[TC64_BM];             // candidate threshold of the level being merged (owner -> partner warps, `many` rows)
-  uint32_t idpub[TC64_BM];        // final id of the level (owner -> partner warps)
-  TcExch exch[3][TC64_BM];        // partner slot -> row: top-3 of that warp's 64 columns
-  uint32_t mask[TC64_BM][8];      // candidate bitmask of the `many` rows (each warp writes the 2 words of its 64 columns)
+  uint32_t rowinfo[2][TC64_BM];   // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
+  float thr[2][TC64_BM];          // candidate threshold of the level being merged (owner -> partner warps, `many` rows)
+  uint32_t idpub[2][TC64_BM];     // final id of the level (owner -> partner warps)
+  TcExch exch[2][3][TC64_BM];     // partner slot -> row: top-3 of that warp's columns
+  uint32_t mask[2][TC64_BM][8];   // candidate bitmask of the `many` rows (each warp writes the words of its own columns)
 };
 
 // tc_tma2d (tc_common.cuh) delivered to the same shared-memory offset (data and mbarrier) of every CTA whose bit is set in `mask`
@@ -61,23 +62,27 @@ __device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-// named barriers of one row group (4 warps = 128 threads)
+// named barriers of the warps that share the rows of one row group (4 warps, or 2 when kGrp = 2)
 // position in a ring of n stages: stage index + phase parity, advanced without divisions (n is a run-time parameter)
 struct Tc64Ring {
   uint32_t st, ph, n;
   __device__ __forceinline__ explicit Tc64Ring(int n_) : st(0), ph(0), n((uint32_t)n_) {}
   __device__ __forceinline__ void next() { if (++st == n) { st = 0; ph ^= 1u; } }
 };
-__device__ __forceinline__ void tc64_grp_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void tc64_grp_arrive(int id) {
+__device__ __forceinline__ void tc64_grp_sync(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
+__device__ __forceinline__ void tc64_grp_arrive(int id, int nthr) {
   __threadfence_block();
-  asm volatile("bar.arrive %0, 128;" ::"r"(id) : "memory");
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthr) : "memory");
 }
 
 // kCl = cluster size.  2: one CTA pair per cluster, every pair streams the codebook blocks from L2 by itself.
 // 4 / 8: two / four pairs per cluster share every block: each of the CTAs that need a given 16 KB half-block loads one slice
 // of it and multicasts it to all of them (1/2, 1/4 of the L2 reads per row; the pairs couple only through the B ring's depth).
-template <bool kTrace, int kCl>
+// kGrp = epilogue groups.  1: all 8 epilogue warps work on the same tile (4 warps per row, 64 columns each).  2: two groups of
+// 4 warps take ALTERNATE tiles (2 warps per row, 128 columns each): the dependency chain of one tile -- scan, merge, serial
+// exact re-ranks, ids, next level's Gram pointers (it, not any chip-wide throughput, is what bounds the
+// kernel) -- gets longer, but two chains overlap; the 4 accumulator buffers already hold both tiles' levels.
+template <bool kTrace, int kCl, int kGrp>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                             // [TC_MAX_KC][8 KB]
@@ -107,8 +112,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
       mbar_init(&ms->b_peer[i], 1);
     }
     for (int i = 0; i < TC64_MAXS; ++i) { mbar_init(&ms->x_full[i], 1); mbar_init(&ms->x_empty[i], TC_NCONV_WARPS); }
-    for (int i = 0; i < TC64_NBUF; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS); }
-    mbar_init(&ms->rowinfo_free, TC64_BM);       // the owner thread of every row
+    for (int i = 0; i < TC64_NBUF; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS / kGrp); }
+    mbar_init(&ms->rowinfo_free[0], TC64_BM);    // the owner thread of every row
+    mbar_init(&ms->rowinfo_free[1], TC64_BM);
     fence_mbar_init();
   }
   if (warp == 1) tc_alloc2(&ms->tmem_base, 512);
@@ -246,7 +252,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         }
         if (kc == nkc - 1) {
           // row statistics for the margin: reduce over the 16 lanes that share a row, publish before the last arrive
-          mbar_wait_guarded(&ms->rowinfo_free, (it & 1) ^ 1, 6);
+          const uint32_t gi = kGrp == 2 ? (it & 1u) : 0u;                    // which group will score this tile
+          const uint32_t gu = kGrp == 2 ? (it >> 1) : it;                    // how many tiles that group has taken before
+          mbar_wait_guarded(&ms->rowinfo_free[gi], (gu & 1u) ^ 1u, 6);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
               sm[j] = fmaxf(sm[j], __shfl_xor_sync(0xffffffffu, sm[j], o));
               s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
             }
-            if (q == 0) ms->rowinfo[16 * cw + 2 * j + hi] = (tc_bf16_up(sm[j]) << 16) | tc_bf16_up(s2[j]);
+            if (q == 0) ms->rowinfo[gi][16 * cw + 2 * j + hi] = (tc_bf16_up(sm[j]) << 16) | tc_bf16_up(s2[j]);
           }
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -269,37 +277,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
   } else {
     // ============================================================== warpgroups 2-3: scores -> candidates -> exact re-rank -> ids
     tc_setmaxnreg_inc<176>();
+    constexpr int NSUB = 2 / kGrp;                      // column ranges per 128-column lane half
+    constexpr int COLS = 128 / NSUB;                    // columns a thread scans: 64 (kGrp = 1) or 128 (kGrp = 2)
+    constexpr int NP = 2 * NSUB - 1;                    // partner warps per row: 3 or 1
+    constexpr int NTHR = 32 * (NP + 1);                 // threads of the named barriers below
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
-    const int sub = (warp - (4 + TC_NCONV_WARPS)) >> 2; // which 64 of the 128 columns
+    const int whi = (warp - (4 + TC_NCONV_WARPS)) >> 2; // upper / lower four epilogue warps
+    const int sub = kGrp == 1 ? whi : 0;                // which COLS of the 128 columns
+    const int grp = kGrp == 1 ? 0 : whi;                // which epilogue group (takes tiles it = grp, grp + kGrp, ...)
     const int rowgrp = quarter & 1, chalf = quarter >> 1;
     const int r_local = rowgrp * 32 + lane;
-    const int cb = tc64_code_base(quarter, sub);        // first code this thread scores
+    const int cb = chalf * 128 + sub * COLS;            // first code this thread scores (tc64_layout.cuh for kGrp = 1)
     const bool owner = (chalf == 0 && sub == 0);
-    const int slot = chalf * 2 + sub - 1;               // partner slot 0..2 (unused by the owner)
+    const int slot = chalf * NSUB + sub - 1;            // partner slot 0..NP-1 (unused by the owner)
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int bar_x = 2 + rowgrp;       // partners -> owner: exch[] written
-    const int bar_m = 4 + rowgrp;       // owner -> partners: thr[] / many_word written
-    const int bar_k = 6 + rowgrp;       // partners -> owner: mask[] words written (only when many_word != 0)
-    const int bar_i = 8 + rowgrp;       // owner -> partners: the level's id is final
+    // three named barriers per (group, row group); every phase needs the owner AND the partners, and consecutive phases on the
+    // same id are separated by a phase on another id that the other side must join first, so no phase can complete early
+    const int bar_a = 2 + (grp * 2 + rowgrp) * 3;   // partners -> owner: exch[] written;  later, partners -> owner: mask[] words written
+    const int bar_b = bar_a + 1;                    // owner -> partners: thr[] / many_word written
+    const int bar_c = bar_a + 2;                    // owner -> partners: the level's id is final
     const int D = p.D;
     const int lane4 = lane * 4;
-    uint32_t g = 0, it = 0;
     TC_EV_DECL();
-    const int ev_role = 2 + sub;        // lane quarter 0 only
+    const int ev_role = 2 + whi;        // lane quarter 0 only
     auto release_tmem = [&](uint32_t buf) {   // one arrive per warp on the LEADER's barrier
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cluster_map(smem_u32(&ms->t_empty[buf]), leader));
     };
 #pragma unroll 1
-    for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
+    for (uint32_t it = (uint32_t)grp; (int)(u_first + it * u_step) < u_count; it += kGrp) {
+      const int unit = u_first + (int)it * u_step;
       const int tile = kCl * unit + (int)rank;
       const int row = tile * TC64_BM + r_local;
       const bool valid = row < p.B;    // rows past B run the same code on zero scores; nothing of theirs is stored
       uint64_t idpack = 0;             // 8 bits per level
       float x4s = 0.f, x2s = 0.f;
 #pragma unroll 1
-      for (int l = 0; l < L; ++l, ++g) {
+      for (int l = 0; l < L; ++l) {
+        const uint32_t g = it * (uint32_t)L + (uint32_t)l;      // position in the MMA issuer's level sequence
         const uint32_t buf = g % TC64_NBUF, u = g / TC64_NBUF;
         const int tri = l * (l - 1) / 2;
         auto grow = [&](int j) -> const float* {
@@ -337,16 +353,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
         if (quarter == 0) TC_EV(ev_role, 1, it * 16 + l);
         tc_fence_after();
-        const uint32_t tcol = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * 64;
+        const uint32_t tcol = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * COLS;
         uint32_t s0[16], s1[16];
         tc_ld16_issue(tcol, s0);
         const TcLevelConst lc = p.hdr->lv[l];
         if (l == 0 && owner) {           // only the merging warp needs the margin
-          const uint32_t ri = ms->rowinfo[r_local];
+          const uint32_t ri = ms->rowinfo[grp][r_local];
           const float xmax = __uint_as_float(ri & 0xffff0000u);        // max|x| (bf16, rounded up)
           x2s = __uint_as_float(ri << 16);                              // sum x^2 (bf16, rounded up; NaN if any input is)
           x4s = (xmax * p.sx < 65504.f) ? xmax * xmax * x2s : INFINITY;  // sum x^4 <= max|x|^2 sum x^2; fp16 overflow/inf -> poison
-          mbar_arrive(&ms->rowinfo_free);
+          mbar_arrive(&ms->rowinfo_free[grp]);
         }
         // ---- margin (DESIGN.md "filter error bound"), identical to rq_tc_kernel
         const float x2n = sqrtf(x2s);
@@ -373,29 +389,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           }
         };
         fold_t(ta0, tb0, cb);
-        // software pipeline over the thread's 64 columns, two 16-column chunks per trip (same body as rq_tc_kernel)
+        // software pipeline over the thread's COLS columns, two 16-column chunks per trip (same body as rq_tc_kernel)
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
+        for (int c = 0; c < COLS; c += 32) {
           load_t(ta1, tb1, cb + c + 16);
           tc_ld_wait();                                   // s0 landed
           tc_ld16_issue(tcol + c + 16, s1);
           score16(s0, ta0, cb + c);
           fold_t(ta1, tb1, cb + c + 16);
-          load_t(ta0, tb0, cb + 32);                      // the last trip harmlessly re-fetches chunk 32 (no branch: see rq_tc.cu)
+          const int cn = min(c + 32, COLS - 32);          // the last trip harmlessly re-fetches its own first chunk (no branch: see rq_tc.cu)
+          load_t(ta0, tb0, cb + cn);
           tc_ld_wait();                                   // s1 landed
-          tc_ld16_issue(tcol + 32, s0);
+          tc_ld16_issue(tcol + cn, s0);
           score16(s1, ta1, cb + c + 16);
-          fold_t(ta0, tb0, cb + 32);
+          fold_t(ta0, tb0, cb + cn);
         }
         tc_ld_wait();
         if (quarter == 0) TC_EV(ev_role, 2, it * 16 + l);
 
-        // exact candidate bitmask of this warp's 64 columns for the rows of the group with >= 3 candidates (warp-uniform
+        // exact candidate bitmask of this warp's columns for the rows of the group with >= 3 candidates (warp-uniform
         // call: tcgen05.ld is .aligned); rows that are not `many` skip the global store only
         auto many_mask = [&](float thr, bool is_many) {
-          const uint32_t tall = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * 64;
+          const uint32_t tall = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * COLS;
 #pragma unroll 1
-          for (int w = 0; w < 2; ++w) {
+          for (int w = 0; w < COLS / 32; ++w) {
             uint32_t mw = 0;
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
@@ -414,32 +431,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
               }
               mw |= bits << (hh * 16);
             }
-            if (is_many) ms->mask[r_local][(cb >> 5) + w] = mw;
+            if (is_many) ms->mask[grp][r_local][(cb >> 5) + w] = mw;
           }
         };
 
         if (!owner) {
           // ---- hand this warp's top-3 to the owner, then follow its verdict
           TcExch e; e.m1 = m1; e.m2 = m2; e.m3 = m3; e.idx = (uint32_t)i1 | ((uint32_t)i2 << 8);
-          ms->exch[slot][r_local] = e;
-          tc64_grp_arrive(bar_x);
-          tc64_grp_sync(bar_m);
-          const uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->many_word[rowgrp]);
+          ms->exch[grp][slot][r_local] = e;
+          tc64_grp_arrive(bar_a, NTHR);
+          tc64_grp_sync(bar_b, NTHR);
+          const uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->many_word[grp][rowgrp]);
           if (mw) {
-            many_mask(*reinterpret_cast<volatile float*>(&ms->thr[r_local]), (mw >> lane) & 1);
-            tc64_grp_arrive(bar_k);
+            many_mask(*reinterpret_cast<volatile float*>(&ms->thr[grp][r_local]), (mw >> lane) & 1);
+            tc64_grp_arrive(bar_a, NTHR);
           }
           release_tmem(buf);
-          tc64_grp_sync(bar_i);
+          tc64_grp_sync(bar_c, NTHR);
           if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
-          idpack |= (uint64_t)(*reinterpret_cast<volatile uint32_t*>(&ms->idpub[r_local]) & 0xff) << (8 * l);
+          idpack |= (uint64_t)(*reinterpret_cast<volatile uint32_t*>(&ms->idpub[grp][r_local]) & 0xff) << (8 * l);
           continue;
         }
 
-        tc64_grp_sync(bar_x);
+        tc64_grp_sync(bar_a, NTHR);
 #pragma unroll
-        for (int sidx = 0; sidx < 3; ++sidx) {
-          const TcExch e = ms->exch[sidx][r_local];
+        for (int sidx = 0; sidx < NP; ++sidx) {
+          const TcExch e = ms->exch[grp][sidx][r_local];
           tc_insert(e.m1, (int)(e.idx & 0xff), m1, m2, m3, i1, i2);
           tc_insert(e.m2, (int)((e.idx >> 8) & 0xff), m1, m2, m3, i1, i2);
           m3 = fminf(m3, fmaxf(m2, e.m3));
@@ -449,13 +466,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         const bool many = flagged && !(m3 > thr);           // >= 3 candidates: rare, needs the full candidate mask
         const uint32_t fl = __ballot_sync(0xffffffffu, flagged);
         const uint32_t mn = __ballot_sync(0xffffffffu, many);
-        ms->thr[r_local] = thr;
-        if (lane == 0) ms->many_word[rowgrp] = mn;
-        tc64_grp_arrive(bar_m);
+        ms->thr[grp][r_local] = thr;
+        if (lane == 0) ms->many_word[grp][rowgrp] = mn;
+        tc64_grp_arrive(bar_b, NTHR);
         if (quarter == 0) TC_EV(ev_role, 3, it * 16 + l);
         if (mn) {
           many_mask(thr, many);
-          tc64_grp_sync(bar_k);          // the partners' mask words are in
+          tc64_grp_sync(bar_a, NTHR);    // the partners' mask words are in
         }
         release_tmem(buf);
         if (quarter == 0) TC_EV(ev_role, 4, it * 16 + l);
@@ -514,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           } else {
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
-              uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->mask[rowgrp * 32 + src][c]);
+              uint32_t mw = *reinterpret_cast<volatile uint32_t*>(&ms->mask[grp][rowgrp * 32 + src][c]);
 #pragma unroll 1
               while (mw) {
                 const int k = c * 32 + __ffs(mw) - 1;
@@ -539,8 +556,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           atomicAdd(p.stats + 2, __popc(mn));
         }
         idpack |= (uint64_t)(my_id & 0xff) << (8 * l);
-        ms->idpub[r_local] = (uint32_t)my_id;     // publish the final id of this level to the partner warps
-        tc64_grp_arrive(bar_i);
+        ms->idpub[grp][r_local] = (uint32_t)my_id;     // publish the final id of this level to the partner warps
+        tc64_grp_arrive(bar_c, NTHR);
         if (quarter == 0) TC_EV(ev_role, 5, it * 16 + l);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
       }
@@ -556,9 +573,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
   }
 }
 
-template <bool kTrace, int kCl>
+template <bool kTrace, int kCl, int kGrp>
 static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = rq_tc64_kernel<kTrace, kCl>;
+  auto kern = rq_tc64_kernel<kTrace, kCl, kGrp>;
   RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -573,6 +590,12 @@ static int tc64_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st
   RQB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   RQB_LAUNCH_CHECK();
   return RQB_OK;
+}
+
+template <int kCl>
+static int tc64_pick(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, int groups) {
+  if (groups == 2) return trace ? tc64_launch<true, kCl, 2>(p, grid, smem, st) : tc64_launch<false, kCl, 2>(p, grid, smem, st);
+  return trace ? tc64_launch<true, kCl, 1>(p, grid, smem, st) : tc64_launch<false, kCl, 1>(p, grid, smem, st);
 }
 
 // p: everything filled in by rqb200_tokenize_tc_run except the tensor maps.  Requires 16-byte aligned rows (x & 15 == 0,
@@ -596,6 +619,8 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
     return RQB_ERR_INVALID;
   }
   p.nb = env_nb; p.nx = env_nx;
+  // epilogue groups (kGrp): 1 = all eight epilogue warps on one tile, 2 = two groups of four on alternate tiles
+  static const int groups = []() { const char* e = getenv("RQB200_TC64_GROUPS"); return (e && e[0] == '2') ? 2 : 1; }();
   const size_t smem = (size_t)TC_MAX_KC * TC64_ACHUNK_BYTES + (size_t)p.nb * TC_BSTAGE_BYTES +
                       (size_t)p.nx * TC64_XSTAGE_BYTES + sizeof(Tc64Misc);
   if ((cluster == 4 || cluster == 8) && ntiles64 > 2) {
@@ -603,7 +628,7 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
     // make this less than sm_count / cluster (queried, not assumed)
     static int max_cl[9] = {0};
     if (max_cl[cluster] == 0) {
-      const void* kern = cluster == 4 ? (const void*)rq_tc64_kernel<false, 4> : (const void*)rq_tc64_kernel<false, 8>;
+      const void* kern = cluster == 4 ? (const void*)rq_tc64_kernel<false, 4, 1> : (const void*)rq_tc64_kernel<false, 8, 1>;
       RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)(sm_count / cluster * cluster));
@@ -620,10 +645,10 @@ int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st
     }
     const int units = (ntiles64 + cluster - 1) / cluster;
     const int ncl = units < max_cl[cluster] ? units : max_cl[cluster];
-    if (cluster == 4) return trace ? tc64_launch<true, 4>(p, 4 * ncl, smem, st) : tc64_launch<false, 4>(p, 4 * ncl, smem, st);
-    return trace ? tc64_launch<true, 8>(p, 8 * ncl, smem, st) : tc64_launch<false, 8>(p, 8 * ncl, smem, st);
+    if (cluster == 4) return tc64_pick<4>(p, 4 * ncl, smem, st, trace, groups);
+    return tc64_pick<8>(p, 8 * ncl, smem, st, trace, groups);
   }
   const int units = (ntiles64 + 1) / 2;
   const int nclusters = units < sm_count / 2 ? units : sm_count / 2;
-  return trace ? tc64_launch<true, 2>(p, 2 * nclusters, smem, st) : tc64_launch<false, 2>(p, 2 * nclusters, smem, st);
+  return tc64_pick<2>(p, 2 * nclusters, smem, st, trace, groups);
 }

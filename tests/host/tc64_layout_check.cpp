@@ -49,6 +49,21 @@ int main() {
       }
   for (int i = 0; i < 64 * 256; ++i) if (tile_hits[i] != 1) ++bad;
   for (int i = 0; i < 64 * 8; ++i) if (word_hits[i] != 1) ++bad;
+  // kGrp = 2 (two epilogue groups on alternate tiles): a warp scans all 128 columns of its lane quarter; the 4 warps of a
+  // group cover the tile once, the mask words of the 2 warps of a row tile [0,8)
+  std::vector<int> tile2(64 * 256, 0), word2(64 * 8, 0);
+  for (int quarter = 0; quarter < 4; ++quarter)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int m = tc64_row_base(quarter) + lane, cb = (quarter >> 1) * 128;
+      for (int c = 0; c < 128; ++c) {
+        const int n = cb + c;
+        if (tc64_tmem_lane(m, n) != quarter * 32 + lane || tc64_tmem_col(n) != c) ++bad;
+        ++tile2[m * 256 + n];
+      }
+      for (int w = 0; w < 4; ++w) ++word2[m * 8 + (cb >> 5) + w];
+    }
+  for (int i = 0; i < 64 * 256; ++i) if (tile2[i] != 1) ++bad;
+  for (int i = 0; i < 64 * 8; ++i) if (word2[i] != 1) ++bad;
   printf("tc64 layout check: bad %d \n", bad);
   return bad != 0;
 }

@@ -161,6 +161,8 @@ UNVALIDATED = {                      # kernel variants written without GPU acces
     "tc64": {"RQB200_TC_64": "1"},            # 64 rows per CTA, M=128 pair MMAs, x staged by TMA; clusters of 2
     "tc64x4": {"RQB200_TC_64": "4"},          # ... clusters of 4: two pairs share the codebook blocks by TMA multicast
     "tc64x8": {"RQB200_TC_64": "8"},          # ... clusters of 8
+    "tc64_g2": {"RQB200_TC_64": "1", "RQB200_TC64_GROUPS": "2"},   # ... two epilogue groups on alternate tiles
+    "tc64x4_g2": {"RQB200_TC_64": "4", "RQB200_TC64_GROUPS": "2"},
     "tma": {"RQB200_TC_TMA": "1"},            # 128-row kernel, x through in-place TMA staging in the A slots
     "tma_pair": {"RQB200_TC_TMA": "1", "RQB200_TC_PAIR": "1"},
 }
