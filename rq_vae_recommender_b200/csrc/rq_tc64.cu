@@ -501,12 +501,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           const bool is_many = (mn >> src) & 1;
           const int ka = min(ci1, ci2), kb = max(ci1, ci2);
           float4 res[6], ev[6], va[6], vb[6];
+          auto prior = [&](int j) { return p.cbf + ((size_t)j * TC_K + (size_t)((rid >> (8 * j)) & 0xff)) * D; };
+          // the x row, both candidates AND the first prior code are requested before anything is consumed: one L2 round trip
+          // less on this serial, critical-path step (a second prefetched prior row was tried: it spills the scan loop)
           ld_row(p.x + (int64_t)rrow * p.ldx, res);        // this kernel is only launched on 16-byte aligned rows
           ld_row(cl + (size_t)ka * D, va);
           ld_row(cl + (size_t)kb * D, vb);
+          if (l >= 1) ld_row(prior(0), ev);
 #pragma unroll 1
           for (int j = 0; j < l; ++j) {
-            ld_row(p.cbf + ((size_t)j * TC_K + (size_t)((rid >> (8 * j)) & 0xff)) * D, ev);
+            if (j >= 1) ld_row(prior(j), ev);
 #pragma unroll
             for (int i = 0; i < 6; ++i) { res[i].x -= ev[i].x; res[i].y -= ev[i].y; res[i].z -= ev[i].z; res[i].w -= ev[i].w; }   // rqvae.py:130, level order
           }
