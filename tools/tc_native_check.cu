@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
         {"", "level start (t_empty ok)", "a_full ok, chunk step", "level issued", "", ""},
         {"", "a_empty/x_full ok, chunk step", "chunk converted+arrived", "", "", ""},
         {"", "t_full ok", "scan end", "merged / verdict out", "tmem released", "level done (re-rank, id out)"},
-        {"", "t_full ok", "scan end", "id received", "", ""}};
+        {"", "t_full ok", "scan end", "id received (partner) / merged (owner, GROUPS=2)", "tmem released", "level done (re-rank, id out)"}};
     printf("timeline of CTA 0 (cycles since first event; payload = tile_index*16 + level-or-step), %zu events\n", recs.size());
     for (const Rec& q : recs) {
       const bool step = (q.role == 0 && q.tag == 2) || q.role == 1;
