@@ -63,6 +63,20 @@ __device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // named barriers of the warps that share the rows of one row group (4 warps, or 2 when kGrp = 2)
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two results; same rounding as the scalar forms).  The
+// scan is instruction-issue bound, and the score / Gram-fold arithmetic is a quarter of its instructions.
+__device__ __forceinline__ void tc64_fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t.reg .b64 pa, pb, pc, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tmov.b64 pc, {%5, %6};\n\t"
+      "fma.rn.f32x2 pd, pa, pb, pc;\n\tmov.b64 {%0, %1}, pd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void tc64_add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 pa, pb;\n\t"
+      "mov.b64 pa, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\t"
+      "add.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 // position in a ring of n stages: stage index + phase parity, advanced without divisions (n is a run-time parameter)
 struct Tc64Ring {
   uint32_t st, ph, n;
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {
           if (l >= 2) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
+            for (int v = 0; v < 4; ++v) { tc64_add2(ta[v].x, ta[v].y, tb[v].x, tb[v].y); tc64_add2(ta[v].z, ta[v].w, tb[v].z, tb[v].w); }
 #pragma unroll 1
             for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
               const float* gj = grow(j) + col;
@@ -375,16 +389,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
 
         float m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
         int i1 = 0, i2 = 0;
+        const uint32_t kmask = p.one ? TCS_KEY_MASK : 0u;      // the key mask in a REGISTER (tcs_pack_reg)
         auto score16 = [&](const uint32_t (&s)[16], const float4 (&t)[4], int col) {
           if (p.one) {   // opaque always-true branch = basic-block boundary (see rq_tc.cu: keeps the prefetches early in SASS)
             float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {      // two scores per insertion: 8 min/max instead of 10 (tc_select.cuh)
-              tcs_key_insert2(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0,
-                              fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
-              tcs_key_insert2(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2,
-                              fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+            // per float4 of Gram/T values: two FFMA2 (two scores each), four one-instruction key packs, two pair insertions
+#define TC64_SCORE4(V)                                                                                                   \
+            {                                                                                                              \
+              float h0, h1, h2, h3;                                                                                        \
+              tc64_fma2(h0, h1, __uint_as_float(s[(V) * 4 + 0]), __uint_as_float(s[(V) * 4 + 1]), ninv, t[V].x, t[V].y);   \
+              tc64_fma2(h2, h3, __uint_as_float(s[(V) * 4 + 2]), __uint_as_float(s[(V) * 4 + 3]), ninv, t[V].z, t[V].w);   \
+              tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 0>(h0, kmask), tcs_pack_reg<(V) * 4 + 1>(h1, kmask), q1, q2, q3); \
+              tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 2>(h2, kmask), tcs_pack_reg<(V) * 4 + 3>(h3, kmask), q1, q2, q3); \
             }
+            TC64_SCORE4(0) TC64_SCORE4(1) TC64_SCORE4(2) TC64_SCORE4(3)
+#undef TC64_SCORE4
             tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
           }
         };

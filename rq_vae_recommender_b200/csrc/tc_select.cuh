@@ -64,13 +64,25 @@ TCS_HD void tcs_key_insert(float a, uint32_t e, float& q1, float& q2, float& q3)
 // the nested fminf).  With lo <= hi the two keys and q1 <= q2 <= q3 the running triple, the k-th smallest of the merged
 // lists is min over i + j = k of max(q_i, key_j):  r1 = min(q1, lo),  r2 = min(max(q1, lo), q2, hi),
 // r3 = min(q3, max(q2, lo), max(q1, hi)).
-TCS_HD void tcs_key_insert2(float a, uint32_t ea, float b, uint32_t eb, float& q1, float& q2, float& q3) {
-  const float ka = tcs_u2f((tcs_f2u(a) & TCS_KEY_MASK) | ea), kb = tcs_u2f((tcs_f2u(b) & TCS_KEY_MASK) | eb);
+TCS_HD void tcs_key_insert2_keys(float ka, float kb, float& q1, float& q2, float& q3) {   // ka, kb: packed keys
   const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
   q3 = fminf(fminf(q3, fmaxf(q2, lo)), fmaxf(q1, hi));
   q2 = fminf(fminf(fmaxf(q1, lo), q2), hi);
   q1 = fminf(q1, lo);
 }
+TCS_HD void tcs_key_insert2(float a, uint32_t ea, float b, uint32_t eb, float& q1, float& q2, float& q3) {
+  tcs_key_insert2_keys(tcs_u2f((tcs_f2u(a) & TCS_KEY_MASK) | ea), tcs_u2f((tcs_f2u(b) & TCS_KEY_MASK) | eb), q1, q2, q3);
+}
+#ifdef __CUDACC__
+// (a & mask) | E in ONE LOP3: with both the mask and the column index as immediates ptxas needs two instructions per key; the
+// mask therefore comes in a register (the caller keeps it opaque) and only E is an immediate.  Same value as the generic form.
+template <uint32_t E>
+__device__ __forceinline__ float tcs_pack_reg(float a, uint32_t mask_in_register) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(a)), "r"(mask_in_register), "n"(E));
+  return __uint_as_float(r);
+}
+#endif
 
 // stage 2: merge the key triple of the chunk whose first column is `cbase` into the running top-3
 TCS_HD void tcs_merge(float q1, float q2, float q3, int cbase, float& m1, float& m2, float& m3, int& i1, int& i2) {
