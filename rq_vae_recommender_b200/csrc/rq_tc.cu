@@ -176,6 +176,7 @@ struct TcSmemMisc {
   uint32_t rowinfo[TC_BM];        // bf16x2 (rounded up): max|x| | sum x^2 of the tile being scored
   TcExch exch[TC_BM];             // half-1 warp -> half-0 warp of the same lane quarter
   uint64_t xs_full, xs_free;      // kTma only: fp32 staging of x landed in the A slots / read out by every converter thread
+  uint32_t conv_sink, conv_pad;   // kTma only: dependency sink of the converters (see tc_conv_sync_after)
 };
 
 
@@ -487,6 +488,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
             asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(hp[i].x), "r"(hp[i].y) : "memory");
           }
         };
+        // Before the barrier every thread STORES a value computed from every packed register (a real side effect: an unused asm
+        // operand is dropped, and without it ptxas sinks most of the packing below the barrier -- seen in SASS -- so that the
+        // loads are still in flight there).
+        auto dep_of = [&](const uint2 (&hp)[8]) {
+          uint32_t d = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d ^= hp[i].x ^ hp[i].y;
+          return d;
+        };
         uint2 pa[8], pb[8];
 #pragma unroll 1
         for (int kc = 0; kc < nkc; ++kc) {
@@ -496,15 +506,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
           lds_half(va, kc);
           if (!last_chunk) lds_half(vb, kc + 1);
           pack_half(va, pa);
-          if (!last_chunk) pack_half(vb, pb);
-          tc_conv_sync();                       // every converter thread HOLDS its staging bytes: the slots may be overwritten
+          uint32_t dep = dep_of(pa);
+          if (!last_chunk) { pack_half(vb, pb); dep ^= dep_of(pb); }
+          tc_conv_sync_after(dep, &ms->conv_sink);   // every converter thread HOLDS its staging bytes: the slots may be overwritten
           if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
           ++ls;
           if (last_chunk) {
             mbar_wait_guarded(&ms->xs_full, ls & 1, 12);
             lds_half(vb, kc);
             pack_half(vb, pb);
-            tc_conv_sync();
+            tc_conv_sync_after(dep_of(pb), &ms->conv_sink);
             if (cw == 0 && lane == 0) mbar_arrive(&ms->xs_free);
             ++ls;
           }

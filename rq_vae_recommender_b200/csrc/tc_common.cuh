@@ -114,6 +114,12 @@ __device__ __forceinline__ void tc_tma2d(void* smem_dst, const CUtensorMap* tmap
 }
 // named barrier 1: the four converter warps (128 threads)
 __device__ __forceinline__ void tc_conv_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// same barrier, preceded by a shared-memory store of `dep`: the caller folds every register that must hold its final value
+// before the barrier into dep; the store cannot be dropped or moved below the barrier, and it cannot issue before those
+// registers (loaded values) have arrived
+__device__ __forceinline__ void tc_conv_sync_after(uint32_t dep, uint32_t* sink) {
+  asm volatile("st.shared.u32 [%0], %1;\n\tbar.sync 1, 128;" ::"r"(smem_u32(sink)), "r"(dep) : "memory");
+}
 
 // mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
