@@ -41,12 +41,21 @@ int main(int argc, char** argv) {
   if (!state_bytes || !prepare || !run || !last_error) { printf("missing symbol\n"); return 2; }
 
   std::vector<float> x((size_t)B * D);
+  // the inputs are cached in /tmp between runs of a session (the generator costs seconds at 65 536 rows, a GPU box is paid by the minute)
+  char cache[256];
+  snprintf(cache, sizeof cache, "/tmp/tc_native_x_%d_%d.bin", B, D);
+  bool cached = false;
+  if (FILE* f = fopen(cache, "rb")) { cached = fread(x.data(), 4, x.size(), f) == x.size(); fclose(f); }
+  if (!cached) {
   for (int b = 0; b < B; ++b) {
     double n2 = 0;
     for (int d = 0; d < D; ++d) { const float v = grand(); x[(size_t)b * D + d] = v; n2 += (double)v * v; }
     const float inv = (float)(1.0 / sqrt(n2));
     for (int d = 0; d < D; ++d) x[(size_t)b * D + d] *= inv;
   }
+  if (FILE* f = fopen(cache, "wb")) { fwrite(x.data(), 4, x.size(), f); fclose(f); }
+  }
+  rng_state = 0x1234567887654321ull ^ (uint64_t)B;      // the codebooks below are drawn from a stream that does not depend on the cache
   // level 0: rows of x plus noise (all codes live); level l: residual-sized random directions
   std::vector<std::vector<float>> cbs(L, std::vector<float>((size_t)K * D));
   for (int l = 0; l < L; ++l)
