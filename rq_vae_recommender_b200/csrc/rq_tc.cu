@@ -188,7 +188,7 @@ struct TcSmemMisc {
 // streams only ITS half of every codebook block (half the L2 and shared-memory traffic per row, and the same 2 x 16 KB ring
 // now covers twice the tensor time).  Barriers the leader waits on (a_full, b_full, t_empty) collect arrivals from both CTAs;
 // barriers the leader signals (a_empty, b_empty, t_full) are multicast commits.
-// kTma = true (RQB200_TC_TMA=1, opt-in, NOT yet run on hardware): x reaches the converter through TMA instead of the LSU path,
+// kOpt bit 0 = kTma (RQB200_TC_TMA=1, opt-in; first hardware run raced, fixed since, fix unrun): x reaches the converter through TMA instead of the LSU path,
 // staged IN PLACE in the A slots the chunk is about to occupy -- there is no other shared memory left in this kernel.  The
 // fp32 source of chunk kc is two 16 KB boxes (128 rows x 32 floats): box 0 lands in slot kc, box 1 in slot kc + 1 (the next
 // chunk's slot, already released by the previous tile); the converters pull both into registers, meet at a named barrier,
@@ -196,8 +196,11 @@ struct TcSmemMisc {
 // The last chunk has no next slot: its two boxes go through its own slot one after the other.  One chunk (32 KB) is in
 // flight at a time, but as bulk copies: no L1TEX miss tracking, no LSU queue shared with the epilogue's gathers (the measured
 // limit of the register path is 5-6 B/clk/SM at a ~6 K-cycle loaded latency).
-template <bool kTrace, bool kVec, bool kPair, bool kTma = false>
+// kOpt bit 1 (RQB200_TC_FASTSCAN=1, opt-in, not yet run): the scan arithmetic of rq_tc64_kernel -- two scores per FFMA2 and per
+// top-3 insertion, one-instruction key packs, FADD2 Gram folds (about 14 -> 10 SASS instructions per score).
+template <bool kTrace, bool kVec, bool kPair, int kOpt = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool kTma = (kOpt & 1) != 0, kFast = (kOpt & 2) != 0;
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sA = tsm;                                         // [nkc][16 KB]  (sized for TC_MAX_KC)
   unsigned char* sB = tsm + TC_MAX_KC * TC_ACHUNK_BYTES;           // [TC_BSTAGES][16 KB]
@@ -655,7 +658,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
         auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {   // called one chunk of compute after load_t
           if (l >= 2) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
+            for (int v = 0; v < 4; ++v) {
+              if constexpr (kFast) { tc_add2(ta[v].x, ta[v].y, tb[v].x, tb[v].y); tc_add2(ta[v].z, ta[v].w, tb[v].z, tb[v].w); }
+              else { ta[v].x += tb[v].x; ta[v].y += tb[v].y; ta[v].z += tb[v].z; ta[v].w += tb[v].w; }
+            }
 #pragma unroll 1
             for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
               const float* gj = grow(j) + col;
@@ -708,12 +714,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
           // pins fix the order in PTX but not in SASS; a block boundary does.
           if (p.one) {
             float q1 = INFINITY, q2 = INFINITY, q3 = INFINITY;
+            if constexpr (kFast) {
+              const uint32_t kmask = p.one ? TCS_KEY_MASK : 0u;      // the key mask in a REGISTER (tcs_pack_reg)
+#define TC_SCORE4(V)                                                                                                     \
+              {                                                                                                            \
+                float h0, h1, h2, h3;                                                                                      \
+                tc_fma2(h0, h1, __uint_as_float(s[(V) * 4 + 0]), __uint_as_float(s[(V) * 4 + 1]), ninv, t[V].x, t[V].y);  \
+                tc_fma2(h2, h3, __uint_as_float(s[(V) * 4 + 2]), __uint_as_float(s[(V) * 4 + 3]), ninv, t[V].z, t[V].w);  \
+                tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 0>(h0, kmask), tcs_pack_reg<(V) * 4 + 1>(h1, kmask), q1, q2, q3); \
+                tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 2>(h2, kmask), tcs_pack_reg<(V) * 4 + 3>(h3, kmask), q1, q2, q3); \
+              }
+              TC_SCORE4(0) TC_SCORE4(1) TC_SCORE4(2) TC_SCORE4(3)
+#undef TC_SCORE4
+            } else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
-              tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+              for (int v = 0; v < 4; ++v) {
+                tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 0]), ninv, t[v].x), v * 4 + 0, q1, q2, q3);
+                tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 1]), ninv, t[v].y), v * 4 + 1, q1, q2, q3);
+                tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 2]), ninv, t[v].z), v * 4 + 2, q1, q2, q3);
+                tcs_key_insert(fmaf(__uint_as_float(s[v * 4 + 3]), ninv, t[v].w), v * 4 + 3, q1, q2, q3);
+              }
             }
             tcs_merge(q1, q2, q3, col, m1, m2, m3, i1, i2);
           }
@@ -919,9 +939,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc_kernel(const __grid_const
   }
 }
 
-template <bool kTrace, bool kVec, bool kPair, bool kTma = false>
+template <bool kTrace, bool kVec, bool kPair, int kOpt = 0>
 static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kern = rq_tc_kernel<kTrace, kVec, kPair, kTma>;
+  auto kern = rq_tc_kernel<kTrace, kVec, kPair, kOpt>;
   RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (kPair) {
     cudaLaunchConfig_t cfg{};
@@ -943,8 +963,11 @@ static int tc_launch(const TcParams& p, int grid, size_t smem, cudaStream_t st) 
 }
 
 template <bool kPair>
-static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, bool vec_ok, bool tma) {
-  if (tma && vec_ok) return trace ? tc_launch<true, true, kPair, true>(p, grid, smem, st) : tc_launch<false, true, kPair, true>(p, grid, smem, st);
+static int tc_dispatch(const TcParams& p, int grid, size_t smem, cudaStream_t st, bool trace, bool vec_ok, int opt) {
+  // opt: bit 0 = in-place TMA staging of x, bit 1 = fast scan arithmetic (both opt-in, vector-load instantiation only)
+  if (vec_ok && opt == 1) return trace ? tc_launch<true, true, kPair, 1>(p, grid, smem, st) : tc_launch<false, true, kPair, 1>(p, grid, smem, st);
+  if (vec_ok && opt == 2) return trace ? tc_launch<true, true, kPair, 2>(p, grid, smem, st) : tc_launch<false, true, kPair, 2>(p, grid, smem, st);
+  if (vec_ok && opt == 3) return trace ? tc_launch<true, true, kPair, 3>(p, grid, smem, st) : tc_launch<false, true, kPair, 3>(p, grid, smem, st);
   if (trace) return vec_ok ? tc_launch<true, true, kPair>(p, grid, smem, st) : tc_launch<true, false, kPair>(p, grid, smem, st);
   return vec_ok ? tc_launch<false, true, kPair>(p, grid, smem, st) : tc_launch<false, false, kPair>(p, grid, smem, st);
 }
@@ -997,6 +1020,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
     int rc = tc_encode_2d(&p.tmapXh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.x, (uint64_t)D, (uint64_t)B, (uint64_t)ldx * 4, 32, TC_BM);
     if (rc) return rc;
   }
+  static const int opt_fast = []() { const char* e = getenv("RQB200_TC_FASTSCAN"); return (e && e[0] == '1') ? 1 : 0; }();
+  const int opt = (tma ? 1 : 0) | ((opt_fast && vec_ok) ? 2 : 0);
   // CTA-pair variant (cta_group::2): opt-in while it is being brought up
   static const int opt_pair = []() { const char* e = getenv("RQB200_TC_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
   if (opt_pair && p.ntiles >= 2 && sm_count >= 2) {
@@ -1004,8 +1029,8 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
     if (rc) return rc;
     const int npairs = (p.ntiles + 1) / 2;
     const int nclusters = npairs < sm_count / 2 ? npairs : sm_count / 2;
-    return tc_dispatch<true>(p, 2 * nclusters, smem, st, trace, vec_ok, tma);
+    return tc_dispatch<true>(p, 2 * nclusters, smem, st, trace, vec_ok, opt);
   }
   const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-  return tc_dispatch<false>(p, grid, smem, st, trace, vec_ok, tma);
+  return tc_dispatch<false>(p, grid, smem, st, trace, vec_ok, opt);
 }

@@ -63,20 +63,6 @@ __device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // named barriers of the warps that share the rows of one row group (4 warps, or 2 when kGrp = 2)
-// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two results; same rounding as the scalar forms).  The
-// scan is instruction-issue bound, and the score / Gram-fold arithmetic is a quarter of its instructions.
-__device__ __forceinline__ void tc64_fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
-  asm("{\n\t.reg .b64 pa, pb, pc, pd;\n\t"
-      "mov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tmov.b64 pc, {%5, %6};\n\t"
-      "fma.rn.f32x2 pd, pa, pb, pc;\n\tmov.b64 {%0, %1}, pd;\n\t}"
-      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void tc64_add2(float& a0, float& a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 pa, pb;\n\t"
-      "mov.b64 pa, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\t"
-      "add.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
-      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
-}
 // position in a ring of n stages: stage index + phase parity, advanced without divisions (n is a run-time parameter)
 struct Tc64Ring {
   uint32_t st, ph, n;
@@ -348,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         auto fold_t = [&](float4 (&ta)[4], const float4 (&tb)[4], int col) {
           if (l >= 2) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) { tc64_add2(ta[v].x, ta[v].y, tb[v].x, tb[v].y); tc64_add2(ta[v].z, ta[v].w, tb[v].z, tb[v].w); }
+            for (int v = 0; v < 4; ++v) { tc_add2(ta[v].x, ta[v].y, tb[v].x, tb[v].y); tc_add2(ta[v].z, ta[v].w, tb[v].z, tb[v].w); }
 #pragma unroll 1
             for (int j = 2; j < l; ++j) {   // L > 3 only: latency exposed, code kept small
               const float* gj = grow(j) + col;
@@ -397,8 +383,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
 #define TC64_SCORE4(V)                                                                                                   \
             {                                                                                                              \
               float h0, h1, h2, h3;                                                                                        \
-              tc64_fma2(h0, h1, __uint_as_float(s[(V) * 4 + 0]), __uint_as_float(s[(V) * 4 + 1]), ninv, t[V].x, t[V].y);   \
-              tc64_fma2(h2, h3, __uint_as_float(s[(V) * 4 + 2]), __uint_as_float(s[(V) * 4 + 3]), ninv, t[V].z, t[V].w);   \
+              tc_fma2(h0, h1, __uint_as_float(s[(V) * 4 + 0]), __uint_as_float(s[(V) * 4 + 1]), ninv, t[V].x, t[V].y);   \
+              tc_fma2(h2, h3, __uint_as_float(s[(V) * 4 + 2]), __uint_as_float(s[(V) * 4 + 3]), ninv, t[V].z, t[V].w);   \
               tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 0>(h0, kmask), tcs_pack_reg<(V) * 4 + 1>(h1, kmask), q1, q2, q3); \
               tcs_key_insert2_keys(tcs_pack_reg<(V) * 4 + 2>(h2, kmask), tcs_pack_reg<(V) * 4 + 3>(h3, kmask), q1, q2, q3); \
             }

@@ -266,6 +266,20 @@ __device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two results; same rounding as the scalar forms).  The
+// scan is instruction-issue bound, and the score / Gram-fold arithmetic is a quarter of its instructions.
+__device__ __forceinline__ void tc_fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t.reg .b64 pa, pb, pc, pd;\n\t"
+      "mov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tmov.b64 pc, {%5, %6};\n\t"
+      "fma.rn.f32x2 pd, pa, pb, pc;\n\tmov.b64 {%0, %1}, pd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void tc_add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 pa, pb;\n\t"
+      "mov.b64 pa, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\t"
+      "add.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda): a row-major 2-D tensor, no swizzle,
 // out-of-bounds elements read as zero
 typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -163,6 +163,8 @@ UNVALIDATED = {                      # kernel variants written without GPU acces
     "tc64x8": {"RQB200_TC_64": "8"},          # ... clusters of 8
     "tc64_g2": {"RQB200_TC_64": "1", "RQB200_TC64_GROUPS": "2"},   # ... two epilogue groups on alternate tiles
     "tc64x4_g2": {"RQB200_TC_64": "4", "RQB200_TC64_GROUPS": "2"},
+    "fast": {"RQB200_TC_FASTSCAN": "1"},      # 128-row kernel with rq_tc64_kernel's scan arithmetic (FFMA2, pair insertion, 1-LOP3 keys)
+    "tma_fast": {"RQB200_TC_TMA": "1", "RQB200_TC_FASTSCAN": "1"},
     "tma": {"RQB200_TC_TMA": "1"},            # 128-row kernel, x through in-place TMA staging in the A slots
     "tma_pair": {"RQB200_TC_TMA": "1", "RQB200_TC_PAIR": "1"},
 }

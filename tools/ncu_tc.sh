@@ -2,7 +2,7 @@
 # ncu captures of the tokeniser kernels through the Python-free harness (tools/tc_native_check.cu): one `--set full` capture
 # per variant plus the memory-system counters that decide the round-2 question "is the kernel bound by L2 -> SM bytes?"
 # (DESIGN.md 5.2b budget: codebook stream + x + Gram gathers against the L2 throughput cap).
-#   usage (GPU box, repo root):  bash tools/ncu_tc.sh [variant ...]     variant = default | pair | tma | tmapair | 64 | 64x4 | 64x8
+#   usage (GPU box, repo root):  bash tools/ncu_tc.sh [variant ...]     variant = default | pair | fast | tma | tmapair | 64 | 64x4 | 64x8
 # Outputs gpurun_out/ncu_tc_<variant>.ncu-rep and a CSV of the counters below; read them in the build container with
 #   ncu -i gpurun_out/ncu_tc_<variant>.ncu-rep --page raw --csv
 set -u
@@ -13,6 +13,7 @@ for v in "${@:-default 64}"; do
     case $variant in
       default) envs="" ; pat="rq_tc_kernel" ;;
       pair)    envs="RQB200_TC_PAIR=1" ; pat="rq_tc_kernel" ;;
+      fast)    envs="RQB200_TC_FASTSCAN=1" ; pat="rq_tc_kernel" ;;
       tma)     envs="RQB200_TC_TMA=1" ; pat="rq_tc_kernel" ;;
       tmapair) envs="RQB200_TC_TMA=1 RQB200_TC_PAIR=1" ; pat="rq_tc_kernel" ;;
       64)      envs="RQB200_TC_64=1" ; pat="rq_tc64_kernel" ;;

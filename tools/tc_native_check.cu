@@ -95,9 +95,9 @@ int main(int argc, char** argv) {
   se = cudaDeviceSynchronize();
   if (se != cudaSuccess) { printf("timed runs: %s\n", cudaGetErrorString(se)); return 1; }
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
-  const char* v64 = getenv("RQB200_TC_64"); const char* vp = getenv("RQB200_TC_PAIR"); const char* vt = getenv("RQB200_TC_TMA"); const char* vg = getenv("RQB200_TC64_GROUPS");
-  printf("B=%d D=%d L=%d TC_64=%s GROUPS=%s TC_PAIR=%s TC_TMA=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
-         B, D, L, v64 ? v64 : "-", vg ? vg : "-", vp ? vp : "-", vt ? vt : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
+  const char* v64 = getenv("RQB200_TC_64"); const char* vp = getenv("RQB200_TC_PAIR"); const char* vt = getenv("RQB200_TC_TMA"); const char* vg = getenv("RQB200_TC64_GROUPS"); const char* vf = getenv("RQB200_TC_FASTSCAN");
+  printf("B=%d D=%d L=%d TC_64=%s GROUPS=%s TC_PAIR=%s TC_TMA=%s FASTSCAN=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
+         B, D, L, v64 ? v64 : "-", vg ? vg : "-", vp ? vp : "-", vt ? vt : "-", vf ? vf : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
          B / (ms / iters) * 1e-3);
   // RQB200_TC_TRACE=1: one more run with the event timeline of CTA 0 switched on (stats[3] = stats[4] = 1, >= 4096 ints; the
   // records are (tag << 56 | payload << 48 | clock) at ((long long*)(stats + 128))[role * 256 ...], see TC_EV in tc_common.cuh)
