@@ -159,22 +159,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       uint32_t g = 0, it = 0;
       Tc64Ring rb(p.nb);
+      long long w_te = 0, w_af = 0, w_bf = 0, w_issue = 0;     // RQB200_TC_TRACE=1: where the issuer's cycles go
       TC_EV_DECL();
+      TC_T0(tm);
+      const long long tm_start = tm;
       for (int unit = u_first; unit < u_count; unit += u_step, ++it)
         for (int l = 0; l < L; ++l, ++g) {
           const uint32_t buf = g % TC64_NBUF, u = g / TC64_NBUF;
+          TC_ACC(w_issue, tm);
           mbar_wait_guarded_cluster(&ms->t_empty[buf], (u & 1) ^ 1, 2);
+          TC_ACC(w_te, tm);
           TC_EV(0, 1, it * 16 + l);
           tc_fence_after();
           const uint32_t d_tmem = TC64_TMEM_BASE() + buf * 128;
           for (int kc = 0; kc < nkc; ++kc, rb.next()) {
+            TC_ACC(w_issue, tm);
             if (l == 0) {
               mbar_wait_guarded_cluster(&ms->a_full[kc], it & 1, 3);
               TC_EV(0, 2, it * 16 + kc);
             }
+            TC_ACC(w_af, tm);
             const uint32_t st = rb.st;
             mbar_wait_guarded_cluster(&ms->b_full[st], rb.ph, 4);
             if constexpr (kCl > 2) mbar_wait_guarded_cluster(&ms->b_peer[st], rb.ph, 10);
+            TC_ACC(w_bf, tm);
             tc_fence_after();
             const uint64_t adesc = tc_smem_desc(a_base + kc * TC64_ACHUNK_BYTES);
             const uint64_t bdesc = tc_smem_desc(b_base + st * TC_BSTAGE_BYTES);
@@ -190,6 +198,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           }
           TC_EV(0, 3, it * 16 + l);
         }
+      if (trace && lane == 0) {      // same slots as rq_tc_kernel (tools/trace_tc.py, tools/tc_native_check.cu)
+        tc_trace_add(p.stats, 0, w_te); tc_trace_add(p.stats, 1, w_af); tc_trace_add(p.stats, 2, w_bf);
+        tc_trace_add(p.stats, 3, clock64() - tm_start); tc_trace_add(p.stats, 12, 1);
+      }
     } else if (warp == 2) {
       // x producer: one 64-row x 64-float box per k chunk.  Rows past B read as zero (tensor-map bounds); a pair's second
       // CTA past the last 64-row tile loads the last tile again (its scores are never stored).
@@ -226,7 +238,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     const int hi = lane >> 4, q = lane & 15;
     uint32_t it = 0;
     Tc64Ring rx(p.nx);
+    long long c_wx = 0, c_wa = 0;     // RQB200_TC_TRACE=1: waiting for the x stage / for the A slot
     TC_EV_DECL();
+    const long long tcv_start = trace ? clock64() : 0;
 #pragma unroll 1
     for (int unit = u_first; unit < u_count; unit += u_step, ++it) {
       float sm[8], s2[8];
@@ -235,8 +249,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
 #pragma unroll 1
       for (int kc = 0; kc < nkc; ++kc, rx.next()) {
         const uint32_t st = rx.st;
-        mbar_wait_guarded(&ms->x_full[st], rx.ph, 9);
-        mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);     // the last level of the previous tile released this chunk
+        {
+          const long long t_in = trace ? clock64() : 0;
+          mbar_wait_guarded(&ms->x_full[st], rx.ph, 9);
+          const long long t_x = trace ? clock64() : 0;
+          mbar_wait_guarded(&ms->a_empty[kc], (it & 1) ^ 1, 5);   // the last level of the previous tile released this chunk
+          if (trace) { c_wx += t_x - t_in; c_wa += clock64() - t_x; }
+        }
         if (cw == 0) TC_EV(1, 1, it * 16 + kc);
         const unsigned char* xs = sX + st * TC64_XSTAGE_BYTES;
         const uint32_t a_chunk = smem_u32(sA) + kc * TC64_ACHUNK_BYTES;
@@ -274,6 +293,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         if (cw == 0) TC_EV(1, 2, it * 16 + kc);
       }
     }
+    if (trace && cw == 0 && lane == 0) {
+      tc_trace_add(p.stats, 9, c_wa); tc_trace_add(p.stats, 20, c_wx); tc_trace_add(p.stats, 10, clock64() - tcv_start);
+    }
   } else {
     // ============================================================== warpgroups 2-3: scores -> candidates -> exact re-rank -> ids
     tc_setmaxnreg_inc<176>();
@@ -300,6 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
     const int lane4 = lane * 4;
     TC_EV_DECL();
     const int ev_role = 2 + whi;        // lane quarter 0 only
+    long long e_tf = 0, e_scan = 0, e_part = 0, e_rr = 0;   // RQB200_TC_TRACE=1 (owner warps of lane quarter 0)
+    TC_T0(te);
+    const long long te_start = te;
     auto release_tmem = [&](uint32_t buf) {   // one arrive per warp on the LEADER's barrier
       tc_fence_before();
       __syncwarp();
@@ -350,7 +375,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         };
         float4 ta0[4], tb0[4], ta1[4], tb1[4];
         load_t(ta0, tb0, cb);            // in flight across the accumulator wait below
+        TC_ACC(e_rr, te);
         mbar_wait_guarded(&ms->t_full[buf], u & 1, 7);
+        TC_ACC(e_tf, te);
         if (quarter == 0) TC_EV(ev_role, 1, it * 16 + l);
         tc_fence_after();
         const uint32_t tcol = TC64_TMEM_BASE() + lane_addr + buf * 128 + sub * COLS;
@@ -410,6 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
           fold_t(ta0, tb0, cb + cn);
         }
         tc_ld_wait();
+        TC_ACC(e_scan, te);
         if (quarter == 0) TC_EV(ev_role, 2, it * 16 + l);
 
         // exact candidate bitmask of this warp's columns for the rows of the group with >= 3 candidates (warp-uniform
@@ -459,6 +487,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         }
 
         tc64_grp_sync(bar_a, NTHR);
+        TC_ACC(e_part, te);
 #pragma unroll
         for (int sidx = 0; sidx < NP; ++sidx) {
           const TcExch e = ms->exch[grp][sidx][r_local];
@@ -570,6 +599,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
         if (quarter == 0) TC_EV(ev_role, 5, it * 16 + l);
         if (valid) p.ids[(int64_t)row * L + l] = my_id;
       }
+    }
+    if (trace && quarter == 0 && owner && lane == 0) {     // one owner warp per group: slots 4..8 (group 0) / 13..17 (group 1)
+      TC_ACC(e_rr, te);
+      const int o = whi ? 13 : 4;
+      tc_trace_add(p.stats, o + 0, e_tf); tc_trace_add(p.stats, o + 1, e_scan); tc_trace_add(p.stats, o + 2, e_part);
+      tc_trace_add(p.stats, o + 3, e_rr); tc_trace_add(p.stats, o + 4, clock64() - te_start);
     }
   }
 

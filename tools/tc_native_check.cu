@@ -110,6 +110,18 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     std::vector<int> tr(4096);
     CK(cudaMemcpy(tr.data(), dtr, 4096 * 4, cudaMemcpyDeviceToHost));
+    // cycle accounting of the traced instantiation (64-bit accumulators from stats[8]; slot 12 = number of MMA-issuing CTAs)
+    {
+      const long long* acc = reinterpret_cast<const long long*>(tr.data() + 8);
+      static const struct { int slot; const char* name; } names[] = {
+          {0, "mma wait t_empty"}, {1, "mma wait a_full"}, {2, "mma wait b_full"}, {3, "mma total"},
+          {9, "conv wait A slot (a_empty)"}, {20, "conv wait x (loads landed / x_full)"}, {21, "conv convert+store"}, {10, "conv total"},
+          {4, "epi0 wait t_full"}, {5, "epi0 scan"}, {6, "epi0 wait partner warps"}, {7, "epi0 merge+many+rerank"}, {8, "epi0 total"},
+          {13, "epi1 wait t_full"}, {14, "epi1 scan"}, {15, "epi1 wait"}, {16, "epi1 other"}, {17, "epi1 total"}};
+      const double nb = acc[12] > 0 ? (double)acc[12] : 1.0;
+      printf("cycle accounting per MMA-issuing CTA (%lld of them):\n", acc[12]);
+      for (const auto& n : names) printf("  %-38s %12.0f\n", n.name, (double)acc[n.slot] / nb);
+    }
     const long long* ev = reinterpret_cast<const long long*>(tr.data() + 128);
     struct Rec { long long clk; int role, tag, pay; };
     std::vector<Rec> recs;
