@@ -167,6 +167,7 @@ UNVALIDATED = {                      # kernel variants written without GPU acces
     "tma_fast": {"RQB200_TC_TMA": "1", "RQB200_TC_FASTSCAN": "1"},
     "tma": {"RQB200_TC_TMA": "1"},            # 128-row kernel, x through in-place TMA staging in the A slots
     "tma_pair": {"RQB200_TC_TMA": "1", "RQB200_TC_PAIR": "1"},
+    "tma_pair_fast": {"RQB200_TC_TMA": "1", "RQB200_TC_PAIR": "1", "RQB200_TC_FASTSCAN": "1"},   # fewest bytes per row into the SM
 }
 
 

@@ -12,7 +12,8 @@ run default RQB200_TC_64=0
 run fast RQB200_TC_FASTSCAN=1
 run tma RQB200_TC_TMA=1
 run tmapair RQB200_TC_TMA=1 RQB200_TC_PAIR=1
+run tmapairfast RQB200_TC_TMA=1 RQB200_TC_PAIR=1 RQB200_TC_FASTSCAN=1
 run 64 RQB200_TC_64=1
 run 64g2 RQB200_TC_64=1 RQB200_TC64_GROUPS=2
 run 64x4 RQB200_TC_64=4
-for v in fast tma tmapair 64 64g2 64x4; do cmp /tmp/tl_default.ids /tmp/tl_$v.ids && echo "IDS_IDENTICAL $v"; done
+for v in fast tma tmapair tmapairfast 64 64g2 64x4; do cmp /tmp/tl_default.ids /tmp/tl_$v.ids && echo "IDS_IDENTICAL $v"; done
