@@ -62,13 +62,13 @@ __device__ __forceinline__ void tc64_commit_mask(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-// named barriers of the warps that share the rows of one row group (4 warps, or 2 when kGrp = 2)
 // position in a ring of n stages: stage index + phase parity, advanced without divisions (n is a run-time parameter)
 struct Tc64Ring {
   uint32_t st, ph, n;
   __device__ __forceinline__ explicit Tc64Ring(int n_) : st(0), ph(0), n((uint32_t)n_) {}
   __device__ __forceinline__ void next() { if (++st == n) { st = 0; ph ^= 1u; } }
 };
+// named barriers of the warps that share the rows of one row group (4 warps, or 2 when kGrp = 2)
 __device__ __forceinline__ void tc64_grp_sync(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
 __device__ __forceinline__ void tc64_grp_arrive(int id, int nthr) {
   __threadfence_block();
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tc64_kernel(const __grid_con
               const int blk_row = ((l * 2 + (int)crank) * nkc + kc) * 128;      // first blob row of this CTA's half-block
               if constexpr (kCl == 2) {
                 if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
-                tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, blk_row, cluster_map(smem_u32(&ms->b_full[st]), 0));
+                tc_tma2d_pair(sB + st * TC_BSTAGE_BYTES, &p.tmapB, 0, blk_row, cluster_map(smem_u32(&ms->b_full[st]), leader));
               } else {
                 // this CTA and the CTAs of the other pairs with the same pair-rank need the same half-block: each loads
                 // slice `pair` of it and multicasts it to all of them; every CTA arms its OWN b_full for the 16 KB it receives
