@@ -65,6 +65,35 @@ __global__ void __launch_bounds__(128, 1) stream_kernel(const unsigned char* bas
   cycles[blockIdx.x] = clock64() - t0;
 }
 
+// ---- second question: how many uncoalesced 32-byte gather requests per clock does one SM's L1TEX sustain?  (The epilogue's Gram
+// gathers: every lane its own 128-byte line, LDG.E.256.)  `warps` warps per CTA each issue `n` rounds of `batch` independent
+// 256-bit loads; lane l of warp w reads sector (round-dependent) of row (l + 32 w + 97 * round) % rows of a [rows][1 KB] table
+// that stays in L2 (768 KB, the size of the three Gram tables).
+__global__ void __launch_bounds__(256, 1) gather_kernel(const float* table, int rows, int rounds, long long* cycles, float* sink) {
+  extern __shared__ __align__(1024) unsigned char smem[];        // only there to keep the carve-out the tokeniser runs with
+  (void)smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    float4 lo[4], hi[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {                                // 4 independent 256-bit loads in flight per lane, like the scan at level 2
+      const int row = (lane + 32 * warp + 97 * (r * 4 + b) + 13 * (int)blockIdx.x) % rows;
+      const float* q = table + (size_t)row * 256 + ((r * 4 + b) & 31) * 8;
+      asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=f"(lo[b].x), "=f"(lo[b].y), "=f"(lo[b].z), "=f"(lo[b].w), "=f"(hi[b].x), "=f"(hi[b].y), "=f"(hi[b].z), "=f"(hi[b].w)
+                   : "l"(q));
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc += lo[b].x + hi[b].w;
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 123.456f) sink[0] = acc;
+}
+
 int main() {
   int dev = 0, sms = 0, khz = 0;
   CK(cudaGetDevice(&dev));
@@ -100,5 +129,23 @@ int main() {
                pattern == 0 ? "shared" : pattern == 1 ? "private" : "priv64", chunk, depth, chunk * depth, bpc_slow, bpc_mean,
                bpc_mean * grid * (double)khz * 1e3 / 1e12, grid, ms);
       }
+  // ---- gather request rate
+  {
+    const int rows = 768;                                        // 768 rows x 1 KB = the three Gram tables
+    float *tab, *sink; CK(cudaMalloc(&tab, (size_t)rows * 1024)); CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(tab, 0, (size_t)rows * 1024));
+    CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int warps : {1, 2, 4, 8}) {
+      const int rounds = 4096;
+      gather_kernel<<<sms, warps * 32, 200 * 1024>>>(tab, rows, 64, dcyc, sink);       // warm L2
+      gather_kernel<<<sms, warps * 32, 200 * 1024>>>(tab, rows, rounds, dcyc, sink);
+      CK(cudaDeviceSynchronize());
+      long long cyc[256]; CK(cudaMemcpy(cyc, dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+      double sum = 0; for (int i = 0; i < sms; ++i) sum += (double)cyc[i];
+      const double req = (double)rounds * 4 * 32 * warps;        // 32-byte sector requests per SM
+      printf("gather: %d warps/SM, 4 x LDG.256 in flight per lane, every lane its own line: %.2f requests/clk/SM = %.1f B/clk/SM\n",
+             warps, req / (sum / sms), 32.0 * req / (sum / sms));
+    }
+  }
   return 0;
 }
