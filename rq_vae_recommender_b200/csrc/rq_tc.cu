@@ -1008,11 +1008,11 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
   static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
   const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const bool trace = want_trace && stats;       // tracing: caller passes >= 64 ints; 64-bit cycle accumulators start at stats[8]
-  // 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M = 128 CTA-pair MMAs, x staged by TMA): opt-in, not yet run on hardware
+  // 64-rows-per-CTA kernel (csrc/rq_tc64.cu: M = 128 CTA-pair MMAs, x staged by TMA): opt-in (one hardware run: identical ids, slower)
   // RQB200_TC_64=1: clusters of 2 (one pair); =4 / =8: clusters of 4 / 8 (two / four pairs sharing the codebook blocks by TMA multicast)
   static const int opt_64 = []() { const char* e = getenv("RQB200_TC_64"); return (e && e[0] == '1') ? 2 : (e && e[0] == '4') ? 4 : (e && e[0] == '8') ? 8 : 0; }();
   if (opt_64 && vec_ok && sm_count >= opt_64) return tc64_run(p, sm_count, trace, opt_64, st);
-  // in-place TMA staging of x (kTma instantiation of rq_tc_kernel, single-CTA or pair): opt-in, not yet run on hardware
+  // in-place TMA staging of x (kOpt bit 0 of rq_tc_kernel, single-CTA or pair): opt-in (first hardware run raced; fixed, fix unrun)
   static const int opt_tma = []() { const char* e = getenv("RQB200_TC_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
   const bool tma = opt_tma && vec_ok;
   if (tma) {

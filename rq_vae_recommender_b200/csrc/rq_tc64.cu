@@ -18,9 +18,11 @@
 //   epilogue              8 warps: warp (quarter, sub) scans TMEM lanes [32 quarter, +32), columns [64 sub, +64) = rows
 //                         32 (quarter & 1) + lane, codes 128 (quarter >> 1) + 64 sub + [0,64); the four partial top-3 of a row
 //                         meet in shared memory, the (quarter < 2, sub 0) warp owns merge / re-rank / ids
-// STATUS: written without GPU access at the end of round 1 (the round's GPU budget was spent).  It compiles for sm_100a and
-// its index arithmetic is unit-tested on the host (tests/test_tc64_layout.py), but it has NOT run on hardware: it is opt-in
-// (RQB200_TC_64=1) and bring-up starts with tools/pair64_probe.cu (TMEM layout, TMA box, M=128 pair throughput).
+// STATUS: written without GPU access at the end of round 1.  Its first (and so far only) hardware run -- commit 473cb52, clusters of
+// 2 / 4 / 8, 1 000 and 65 536 rows -- returned ids byte-identical to rq_tc_kernel's and was 16 % slower; the
+// TMEM layout and the full-rate M = 128 pair instruction were confirmed by tools/pair64_probe.cu in the same call.  Ring
+// parameters, the named-barrier scheme, the scan arithmetic and the kGrp = 2 variant were changed AFTER that run: opt-in
+// (RQB200_TC_64), gated test (RQB200_TEST_UNVALIDATED=1), index arithmetic unit-tested on the host (tests/test_tc64_layout.py).
 #include "tc_common.cuh"
 #include "tc64_layout.cuh"
 
