@@ -173,18 +173,23 @@ def rq_tokenize(res: np.ndarray, codebooks: Sequence[np.ndarray]) -> np.ndarray:
     return np.stack(ids, axis=-1)
 
 
-def top2_gap(res64: np.ndarray, codebooks64: Sequence[np.ndarray], ids: Optional[np.ndarray] = None):
+def top2_gap(res64: np.ndarray, codebooks64: Sequence[np.ndarray], ids: Optional[np.ndarray] = None,
+             return_abs: bool = False):
     """float64 tie classifier (SURVEY 8c parity protocol).
 
     Returns (ids64 [B,L], best2 [B,L], relgap [B,L]) where the chain follows ``ids`` if given
     (so level l is judged on the residual the implementation under test actually saw),
-    best2 is the runner-up code and relgap = (d2 - d1) / max(d1, tiny)."""
+    best2 is the runner-up code and relgap = (d2 - d1) / max(d1, tiny).
+    With ``return_abs`` also (d2 - d1) / (||res||^2 + ||c_best||^2): the gap in units of the OPERANDS of
+    quantize.py:113-117's  xx + cc - 2 x.c  -- when a row all but coincides with a code, d1 is a cancellation
+    residue of terms ~1 and fp32 cannot resolve differences below a few 2^-24 of those terms, whatever d1 is."""
     assert res64.dtype == np.float64
     B = res64.shape[0]
     L = len(codebooks64)
     ids64 = np.zeros((B, L), np.int64)
     second = np.zeros((B, L), np.int64)
     gap = np.zeros((B, L), np.float64)
+    absgap = np.zeros((B, L), np.float64)
     res = res64
     for l, cb in enumerate(codebooks64):
         d = quantize_dist(res, cb)
@@ -194,8 +199,12 @@ def top2_gap(res64: np.ndarray, codebooks64: Sequence[np.ndarray], ids: Optional
         ids64[:, l] = order[:, 0]
         second[:, l] = order[:, 1]
         gap[:, l] = (d2 - d1) / np.maximum(np.abs(d1), 1e-30)
+        scale = (res * res).sum(1) + (cb * cb).sum(1)[order[:, 0]]
+        absgap[:, l] = (d2 - d1) / np.maximum(scale, 1e-30)
         follow = ids64[:, l] if ids is None else ids[:, l]
         res = res - cb[follow]
+    if return_abs:
+        return ids64, second, gap, absgap
     return ids64, second, gap
 
 

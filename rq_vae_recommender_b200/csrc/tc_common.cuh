@@ -1,47 +1,58 @@
-// Shared definitions of the tensor-core tokeniser kernels (csrc/rq_tc.cu: 128 rows per CTA; csrc/rq_tc64.cu: 64 rows per
-// CTA under an M=128 CTA-pair instruction): prepared-state layout, kernel parameters, tcgen05 / TMA PTX wrappers.
+// Shared definitions of the tensor-core tokeniser kernels (csrc/rq_tc.cu, csrc/rq_tcx.cu): prepared-state layout, kernel
+// parameters, tcgen05 / TMA PTX wrappers.
 // Everything here is static / inline; the result contract is stated at the top of rq_tc.cu.
 #pragma once
 #include "common.cuh"
-#include "tc_select.cuh"
 #include <cuda.h>        // CUtensorMap (the CTA-pair variants load codebook blocks / x tiles with tensor-map TMA)
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
 
 #define TC_K 256          // codes per level (fixed)
-#define TC_BM 128         // rows per tile
 #define TC_KC 64          // fp16 elements per 128-byte swizzle row
 #define TC_MAX_D 768
 #define TC_MAX_KC (TC_MAX_D / TC_KC)
-#define TC_BSTAGES 2
 #define TC_BSTAGE_BYTES (128 * TC_KC * 2)   // 128 codes x 64 k x fp16 = 16 KB
-#define TC_ACHUNK_BYTES (TC_BM * TC_KC * 2) // 16 KB
 #define TC_NCONV_WARPS 4
 #define TC_NEPI_WARPS 8
 #define TC_THREADS ((4 + TC_NCONV_WARPS + TC_NEPI_WARPS) * 32)   // warpgroups: {producer, MMA, 2 idle} | 4 converters | 8 epilogue (2 per TMEM lane quarter) = 512 threads
-// Margin multiplier on the statistical fp16 rounding bound sigma' (DESIGN.md "filter error bound").  Validated with the
-// sum-x^4 statistic at z = 6 (worst observed error 2.3 sigma' over 12.6 M pairs).  The cheaper statistic now in use,
-// sum x^4 <= max|x|^2 sum x^2, makes sigma' ~1.38x larger on gaussian-like rows, so z = 6 / 1.38 keeps the SAME
-// effective margin that was validated instead of an accidentally wider one (which only adds re-rank work).
-#define TC_Z 4.5f
+// Filter error bound (DESIGN.md 5.2 "filter error bound", tests/tc_filter_model.py): DETERMINISTIC.  With x~ = fp16(x) and
+// c~ = fp16(c 2^s) / 2^s,   x~.c~ - x.c = (x~ - x).c~ + x.(c~ - c)   exactly, hence by Cauchy-Schwarz
+//   |x~.c~_k - x.c_k| <= ||x~ - x|| ||c~_k|| + ||x|| ||c~_k - c_k||  <=  ex_b chat_l + xn_b ec_l
+// ex_b is MEASURED per row by the converter (subnormal flushes and overflow are inside it: an overflowing row gets
+// ex = inf and keeps every code), chat_l / ec_l are measured per level by tc_prep_err_kernel.  TC_INFL covers the fp32
+// accumulation of those norms and the bf16 round-up of the published row statistics.
+#define TC_INFL 1.002f
 
 struct TcLevelConst {
   float sc;      // power-of-two scale applied to the codebook before fp16 conversion
-  float c4max;   // max_k sqrt(sum_d c^4)
-  float c1max;   // max_k sum_d |c|
-  float c2max;   // max_k ||c||_2
-  float gerr;    // bound on the fp32 rounding of the Gram corrections of this level
-  float pad[3];
+  float chat;    // max_k ||c~_k||_2            (x TC_INFL)
+  float ec;      // max_k ||c~_k - c_k||_2      (x TC_INFL)
+  float c2max;   // max_k ||c_k||_2
+  float gerr;    // roundings of the Gram tables / cc / the score FFMA at this level
+  float prior;   // sum_{j<l} c2max_j: bound on the norm of the codes subtracted before this level
+  float pad[2];
 };
 
 struct TcHeader {
   TcLevelConst lv[RQB_MAX_LEVELS];
   unsigned int amax_bits[RQB_MAX_LEVELS];  // scratch of prepare
-  unsigned int c4_bits[RQB_MAX_LEVELS];
-  unsigned int c1_bits[RQB_MAX_LEVELS];
+  unsigned int chat_bits[RQB_MAX_LEVELS];
+  unsigned int ec_bits[RQB_MAX_LEVELS];
   unsigned int c2_bits[RQB_MAX_LEVELS];
 };
+
+// eps_b of level l from the published row statistics (ex^2, xn^2): every term is an upper bound, see tests/tc_filter_model.py
+__host__ __device__ __forceinline__ float tc_eps(const TcLevelConst& lc, float ex2, float xn2) {
+#ifdef __CUDA_ARCH__
+  const float ex = __fsqrt_ru(ex2), xn = __fsqrt_ru(xn2);     // rounded UP: every term stays an upper bound; one MUFU each, no slow path
+#else
+  const float ex = sqrtf(ex2) * 1.0000002f, xn = sqrtf(xn2) * 1.0000002f;
+#endif
+  const float acc = 7.62939453e-6f * xn * lc.c2max;                                             // 2^-17: tensor-core fp32 accumulation
+  const float ref = 7.62939453e-6f * ((xn + lc.prior) * lc.c2max + 0.5f * lc.c2max * lc.c2max); // fp32 noise of the reference's own distances
+  return TC_INFL * (ex * lc.chat + xn * lc.ec) + acc + lc.gerr + ref;
+}
 
 static size_t tc_off_cc(int L) { return rqb_round_up(sizeof(TcHeader), 256); }
 static size_t tc_off_hcc(int L) { return tc_off_cc(L) + rqb_round_up((size_t)L * TC_K * 4, 256); }
@@ -112,15 +123,6 @@ __device__ __forceinline__ void tc_tma2d(void* smem_dst, const CUtensorMap* tmap
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// named barrier 1: the four converter warps (128 threads)
-__device__ __forceinline__ void tc_conv_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-// same barrier, preceded by a shared-memory store of `dep`: the caller folds every register that must hold its final value
-// before the barrier into dep; the store cannot be dropped or moved below the barrier, and it cannot issue before those
-// registers (loaded values) have arrived
-__device__ __forceinline__ void tc_conv_sync_after(uint32_t dep, uint32_t* sink) {
-  asm volatile("st.shared.u32 [%0], %1;\n\tbar.sync 1, 128;" ::"r"(smem_u32(sink)), "r"(dep) : "memory");
-}
-
 // mbarrier arrives when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -151,79 +153,14 @@ __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
-
-// read-only 128-bit load as a VOLATILE asm: keeps its program position relative to the other volatile asm statements
-// (tcgen05.ld / wait), which is what makes the hand-written software pipelines below survive the compiler's code sinking
-__device__ __forceinline__ float4 ldg_pinned(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-
-// 256-bit flavour (sm_100: LDG.E.256), 32-byte aligned address.  The Gram-row gathers of the scan touch a different 128-byte
-// line in every lane, so the L1TEX data pipe spends one wavefront per lane per instruction whatever the access width: ncu
-// showed that pipe as the busiest unit of the kernel (47 %), with the converter's x loads queueing behind the gathers
-// (timeline: 6.6 K cycles from issue to data).  Twice the bytes per lane per instruction = half the wavefronts.
-__device__ __forceinline__ void ldg256_pinned(const float* p, float4& lo, float4& hi) {
-  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-               : "l"(p));
-}
-
-// ------------------------------------------------------------------------------------------------ main kernel
-struct TcParams {
-  CUtensorMap tmapB;    // pair variant: the fp16 codebook blob as a [blocks*128 rows][64 halves] matrix, box = one 16 KB block
-  const float* x;
-  int64_t ldx;
-  int B, D, L, nkc, ntiles;
-  const TcHeader* hdr;
-  const float* cc;      // [L][256]
-  const float* hcc;     // [L][256]  cc / 2
-  const float* gram;    // [L(L-1)/2][256][256]
-  const float* cbf;     // [L][256][D] fp32 codebook copy (exact re-rank), rows 256-byte aligned
-  const unsigned char* blob;
-  int64_t* ids;         // [B][L]
-  int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] level-rows scanned twice
-  float sx;             // scale of the fp16 image of x; fixed at 1 (kept in the margin formulas for a future per-call scale)
-  int rot;              // 1: every CTA walks the k chunks from its own starting chunk (blockIdx % nkc), see tc_rot()
-  int prefetch;         // 1: the producer pulls the next tile's x rows into L2 ahead of the converter
-  int one;              // always 1, opaque to the compiler: `if (p.one)` makes a block boundary ptxas cannot schedule across
-  CUtensorMap tmapX;    // rq_tc64_kernel only: x as a [B][D] fp32 tensor, box = 64 rows x 64 floats (one 16 KB staging stage)
-  CUtensorMap tmapXh;   // rq_tc_kernel<.., kTma>: x as a [B][D] fp32 tensor, box = 128 rows x 32 floats (half a chunk, one A slot)
-  CUtensorMap tmapB2;   // rq_tc64_kernel, clusters of 4: the codebook blob with a 64-row box (8 KB multicast slices)
-  int nb, nx;             // rq_tc64_kernel: depth of the codebook ring / the x staging ring (16 KB stages)
-};
-
-struct TcExch { float m1, m2, m3; uint32_t idx; };   // top-3 half-distances + (i1 | i2 << 8) of one 128-column half
-
-// optional cycle accounting: when stats[3] != 0 the caller passed >= 64 ints; 64-bit accumulators start at stats[8]
-__device__ __forceinline__ void tc_trace_add(int* stats, int slot, long long v) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(stats + 8) + slot, (unsigned long long)v);
-}
 // event timeline of CTA 0 (RQB200_TC_TRACE=1 and stats[4] != 0; the caller passes >= 4096 ints): role r appends
-// (tag << 56 | payload << 48 | clock) records at ((long long*)(stats + 128))[r * 256 ...]; tools/trace_tc.py --timeline prints them
+// (tag << 56 | payload << 48 | clock) records at ((long long*)(stats + 128))[r * 256 ...]; tools/tc_native_check.cu prints them
 #define TC_EV_DECL() int ev_n = 0; const bool ev_on = trace && blockIdx.x == 0 && p.stats[4] != 0
 #define TC_EV(role, tag, payload) do { if (ev_on && (threadIdx.x & 31) == 0 && ev_n < 256) { \
     reinterpret_cast<long long*>(p.stats + 128)[(role) * 256 + ev_n++] = \
         ((long long)(tag) << 56) | ((long long)((payload) & 0xff) << 48) | (clock64() & 0xffffffffffffLL); } } while (0)
-#define TC_T0(var) long long var = trace ? clock64() : 0
-#define TC_ACC(acc, var) do { if (trace) { const long long n__ = clock64(); acc += n__ - var; var = n__; } } while (0)
-
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void tc_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void tc_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void tc_pair_arrive(int id) {
-  __threadfence_block();
-  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
-}
-
 __device__ __forceinline__ uint32_t tc_bf16_up(float v) {   // bf16 bits of the smallest bf16 >= v (v >= 0, inf/nan kept)
   uint32_t b = __float_as_uint(v);
   if ((b & 0x7f800000u) != 0x7f800000u && (b & 0xffffu)) b += 0x10000u;
@@ -254,32 +191,10 @@ __device__ __forceinline__ bool tc_elect_one() {
   return pred != 0;
 }
 
-// k-chunk visited at step i: CTAs start at different chunks so that 148 SMs do not all stream the SAME 16 KB codebook block
-// (same L2 lines) at the same moment.  Only the fp32 summation order of the approximate scores changes, which the margin
-// covers; a tile's order depends on the CTA that owns it, which is fixed for a given launch shape.
-__device__ __forceinline__ int tc_rot(int i, int rot0, int nkc) {
-  const int kc = i + rot0;
-  return kc >= nkc ? kc - nkc : kc;
-}
-
 __device__ __forceinline__ float tc_dot4(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
-// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two results; same rounding as the scalar forms).  The
-// scan is instruction-issue bound, and the score / Gram-fold arithmetic is a quarter of its instructions.
-__device__ __forceinline__ void tc_fma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
-  asm("{\n\t.reg .b64 pa, pb, pc, pd;\n\t"
-      "mov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %4};\n\tmov.b64 pc, {%5, %6};\n\t"
-      "fma.rn.f32x2 pd, pa, pb, pc;\n\tmov.b64 {%0, %1}, pd;\n\t}"
-      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void tc_add2(float& a0, float& a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 pa, pb;\n\t"
-      "mov.b64 pa, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\t"
-      "add.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
-      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
-}
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda): a row-major 2-D tensor, no swizzle,
 // out-of-bounds elements read as zero
 typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -310,12 +225,3 @@ static inline int tc_encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, const vo
   }
   return RQB_OK;
 }
-// the fp16 codebook blob is a sequence of pre-swizzled 16 KB images = 128 rows of 128 bytes each: a [nblocks*128][64] fp16
-// matrix whose box {64, 128} is exactly one image; no swizzle here, the bytes are already in the tcgen05 shared-memory order
-static inline int tc_encode_blob_map(CUtensorMap* tm, const void* blob, int nblocks) {
-  return tc_encode_2d(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, blob, 64, (uint64_t)nblocks * 128, 128, 64, 128);
-}
-
-// rq_tc64.cu: the 64-rows-per-CTA kernel (M = 128 CTA-pair MMAs, x staged by TMA).  `p` carries everything but tmapX / tmapB.
-// cluster = 2: one CTA pair per cluster; 4: two pairs per cluster sharing every codebook block by TMA multicast.
-int tc64_run(TcParams& p, int sm_count, bool trace, int cluster, cudaStream_t st);

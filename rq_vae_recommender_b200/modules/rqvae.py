@@ -182,7 +182,9 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
 
     @torch.no_grad()
     def tokenize(self, x: Tensor, mlp_precision: str = None) -> Tensor:
-        """sem_ids [B,L] only: what SemanticIdTokenizer consumes (semids.py:125), ids-only eval kernel.
+        """sem_ids [B,L] only: what SemanticIdTokenizer consumes (semids.py:125).  Large batches go through the tcgen05
+        candidate filter + exact re-rank (prepared codebook state cached on the codebooks' identity and version; the shipped
+        D = 32 quantiser is zero-padded to 64), small ones through the exact CUDA-core kernel: ops.rq_tokenize_auto.
         ``mlp_precision="bf16"`` runs the encoder on the bf16 tcgen05 GEMMs (faster, NOT index-exact vs fp32)."""
         x = x.to(next(self.encoder.parameters()).dtype)
         if mlp_precision is not None:
@@ -193,7 +195,7 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
                 self.encoder.precision = old
         else:
             res = self.encode(x)
-        return ops.rq_tokenize(res, [layer.codebook() for layer in self.layers])
+        return ops.rq_tokenize_auto(res, [layer.codebook() for layer in self.layers])
 
     def forward(self, batch: SeqBatch, gumbel_t: float) -> RqVaeComputedLosses:
         x = batch.x

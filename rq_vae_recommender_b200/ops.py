@@ -16,6 +16,9 @@ MODE_EVAL, MODE_GUMBEL, MODE_STE, MODE_ROTATION = 0, 1, 2, 3
 
 #: count of librqb200 kernel launches issued through this module (bench.py reports it as `gpu_launches`)
 LAUNCHES = 0
+#: calls of the tensor-core tokeniser / prepared-state builds (tests assert the module API really routes there)
+TC_CALLS = 0
+TC_PREPARES = 0
 
 
 def _count(n: int) -> None:
@@ -397,40 +400,105 @@ def tc_supported(D: int, K: int, L: int) -> bool:
     return bool(_lib.load().rqb200_tokenize_tc_supported(D, K, L))
 
 
+TC_PAD = 64   # the tcgen05 tokeniser wants D % 64 == 0: narrower / odd widths are zero-padded (exact for every dot product)
+
+
+def tc_padded_dim(D: int, K: int, L: int) -> int:
+    """Width the tensor-core tokeniser runs a D-wide quantiser at (D itself, or D zero-padded to the next multiple of 64);
+    0 when the shape cannot use it at all (K != 256, D > 768, L > 8)."""
+    Dp = (D + TC_PAD - 1) // TC_PAD * TC_PAD
+    return Dp if tc_supported(Dp, K, L) else 0
+
+
 class TcState:
-    """Device-side prepared codebooks for the tcgen05 tokeniser (fp16 copies, norms, Gram tables)."""
+    """Device-side prepared codebooks for the tcgen05 tokeniser (fp16 images, measured rounding norms, float64 Gram
+    tables, an fp32 copy for the exact re-rank).  Owns everything it needs: the caller's tensors are not referenced after
+    construction.  Codebooks narrower than a multiple of 64 are zero-padded (``self.D`` is the padded width,
+    ``self.D_in`` the caller's)."""
 
     def __init__(self, codebooks: Sequence[torch.Tensor]):
         lib = _lib.load()
         cbs = _check_codebooks(codebooks, codebooks[0].shape[1])
-        self.K, self.D = cbs[0].shape
+        _need_cuda(*cbs)
+        self.K, self.D_in = cbs[0].shape
         self.L = len(cbs)
-        if not lib.rqb200_tokenize_tc_supported(self.D, self.K, self.L):
-            raise _lib.Rqb200Error(f"tcgen05 tokeniser does not support D={self.D} K={self.K} L={self.L}")
+        self.D = tc_padded_dim(self.D_in, self.K, self.L)
+        if not self.D:
+            raise _lib.Rqb200Error(f"tcgen05 tokeniser does not support D={self.D_in} K={self.K} L={self.L}")
+        if self.D != self.D_in:
+            cbs = [torch.nn.functional.pad(c, (0, self.D - self.D_in)) for c in cbs]
+        self.device = cbs[0].device
         nbytes = lib.rqb200_tokenize_tc_state_bytes(self.D, self.K, self.L)
-        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=cbs[0].device)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.nbytes = nbytes
-        self.codebooks = cbs            # keep alive: the re-rank reads the fp32 originals
-        with torch.cuda.device(self.buf.device):
+        with torch.cuda.device(self.device):
             _lib.check(lib.rqb200_tokenize_tc_prepare(_ptr_array(cbs), self.D, self.K, self.L, _p(self.buf), nbytes,
                                                       _stream()), "tokenize_tc_prepare")
-        _count(3)
+        _count(6 + self.L * (self.L - 1) // 2)
+        global TC_PREPARES
+        TC_PREPARES += 1
 
 
 def rq_tokenize_tc(x: torch.Tensor, codebooks=None, state: Optional[TcState] = None, stats=None) -> torch.Tensor:
-    """sem_ids [B,L] int64 via the tcgen05 candidate filter + exact fp32 re-rank (csrc/rq_tc.cu)."""
+    """sem_ids [B,L] int64 via the tcgen05 candidate filter + exact fp32 re-rank (csrc/rq_tcx.cu).  Same result contract as
+    ``rq_tokenize``: the filter's margin is a deterministic bound on the fp16 rounding, every row with more
+    than one candidate inside it is re-scored with the exact kernel's fp32 arithmetic."""
     _need_cuda(x)
     lib = _lib.load()
     if state is None:
         state = TcState(codebooks)
     x = _rows(x)
     B, D = x.shape
+    if D != state.D_in:
+        raise _lib.Rqb200Error(f"rq_tokenize_tc: x has {D} columns, the prepared state was built for {state.D_in}")
+    if x.device != state.device:
+        raise _lib.Rqb200Error(f"rq_tokenize_tc: x is on {x.device}, the prepared state on {state.device}")
+    if D != state.D:
+        x = torch.nn.functional.pad(x, (0, state.D - D))
+    if x.data_ptr() % 16 or x.stride(0) % 4:        # the kernel reads x through TMA: 16-byte aligned base and row pitch
+        x = x.contiguous()
     ids = torch.empty((B, state.L), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.rqb200_tokenize_tc_run(_p(x), x.stride(0), B, _p(state.buf), D, state.K, state.L, _p(ids),
+        _lib.check(lib.rqb200_tokenize_tc_run(_p(x), x.stride(0), B, _p(state.buf), state.D, state.K, state.L, _p(ids),
                                               _p(stats), _stream()), "tokenize_tc_run")
     _count(1)
+    global TC_CALLS
+    TC_CALLS += 1
     return ids
+
+
+# frozen-codebook cache of prepared states behind the module API (RqVae.tokenize / SemanticIdTokenizer): keyed on the
+# identity AND version of every codebook tensor, so an optimiser step (in-place update bumps ._version) or a reloaded
+# checkpoint re-prepares; a handful of entries is plenty (one model per process in the reference's scripts)
+_TC_CACHE: "dict[tuple, TcState]" = {}
+_TC_CACHE_MAX = 4
+#: rows below which the exact CUDA-core kernel is used even when the tensor-core path is available (one 128-row tile keeps
+#: 2 of 148 SMs busy; the prepare step costs ~0.4 ms when the cache misses)
+TC_MIN_ROWS = 1024
+
+
+def _tc_cache_key(codebooks: Sequence[torch.Tensor]):
+    return tuple((c.data_ptr(), c._version, tuple(c.shape), c.device.index) for c in codebooks)
+
+
+def tc_state_for(codebooks: Sequence[torch.Tensor]) -> TcState:
+    key = _tc_cache_key(codebooks)
+    st = _TC_CACHE.get(key)
+    if st is None:
+        if len(_TC_CACHE) >= _TC_CACHE_MAX:
+            _TC_CACHE.pop(next(iter(_TC_CACHE)))
+        st = _TC_CACHE[key] = TcState(codebooks)
+    return st
+
+
+def rq_tokenize_auto(x: torch.Tensor, codebooks: Sequence[torch.Tensor], stats=None) -> torch.Tensor:
+    """What the module API calls (RqVae.tokenize, SemanticIdTokenizer.precompute_corpus_ids, modules/rqvae.py:118-139 ids
+    only): the tensor-core tokeniser with a cached prepared state whenever the shape allows (K = 256, D <= 768 after
+    zero-padding to a multiple of 64) and the batch is large enough to fill the GPU, else the exact CUDA-core kernel."""
+    K, D = codebooks[0].shape
+    if x.shape[0] >= TC_MIN_ROWS and not torch.is_grad_enabled() and tc_padded_dim(D, K, len(codebooks)):
+        return rq_tokenize_tc(x, state=tc_state_for(codebooks), stats=stats)
+    return rq_tokenize(x, codebooks)
 
 
 # ---------------------------------------------------------------------------------------------- bf16 tensor-core MLP

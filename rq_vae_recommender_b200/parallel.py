@@ -27,7 +27,9 @@ def shard_bounds(n: int, world: int, rank: int):
 
 
 class CorpusTokenizer:
-    """Frozen codebooks -> ids.  ``use_tc`` selects the tcgen05 filter + exact re-rank kernel (prepared once)."""
+    """Frozen codebooks -> ids.  ``use_tc`` selects the tcgen05 filter + exact re-rank kernel (state prepared once; its margin is
+    a deterministic bound, so the result contract is the exact kernel's).  Default: on whenever the shape allows it (K = 256,
+    D <= 768; widths that are not a multiple of 64 are zero-padded)."""
 
     def __init__(self, codebooks: Sequence[torch.Tensor], use_tc: Optional[bool] = None,
                  encoder: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, chunk_rows: int = 16384):
@@ -35,27 +37,34 @@ class CorpusTokenizer:
         self.K, self.D = self.codebooks[0].shape
         self.L = len(self.codebooks)
         if use_tc is None:
-            use_tc = ops.tc_supported(self.D, self.K, self.L)
+            use_tc = bool(ops.tc_padded_dim(self.D, self.K, self.L))
         self.use_tc = bool(use_tc)
         self.state = ops.TcState(self.codebooks) if self.use_tc else None
         self.encoder = encoder
         self.chunk_rows = chunk_rows
         self._copy_stream = None
         self._host_out = None
+        self._ring = None
 
     # ---- device resident rows
     @torch.no_grad()
-    def tokenize_device(self, x: torch.Tensor) -> torch.Tensor:
+    def tokenize_device(self, x: torch.Tensor, stats=None) -> torch.Tensor:
         if self.encoder is not None:
             x = self.encoder(x)
         if self.use_tc:
-            return ops.rq_tokenize_tc(x, state=self.state)
+            return ops.rq_tokenize_tc(x, state=self.state, stats=stats)
         return ops.rq_tokenize(x, self.codebooks)
 
     # ---- host rows in, host ids out (the reference's semids.py:93 copies every 512-row batch H->D)
+    RING = 3
+
     @torch.no_grad()
     def tokenize_host(self, x_host: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Double-buffered: chunk i+1 is copied host->device on a side stream while chunk i is quantised."""
+        """Pipelined over ``chunk_rows`` chunks with a ring of RING device buffers: chunk i+1 (and i+2) are copied host->device
+        on a side stream while chunk i is quantised, and a buffer is refilled only after the kernel that read it has finished,
+        so at most RING chunks (not the corpus) are resident.  ``x_host`` should be pinned for the copies to overlap.
+        Returns ``out`` if given; otherwise the tokenizer's own pinned result buffer, which the NEXT call with the same row
+        count overwrites -- pass ``out=`` (or clone) to keep a result across calls."""
         n = x_host.shape[0]
         dev = self.codebooks[0].device
         if out is None:                       # pinned result buffer, allocated once per size (cudaHostAlloc is slow)
@@ -64,23 +73,38 @@ class CorpusTokenizer:
             out = self._host_out
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+        width = x_host.shape[1]
+        if self._ring is None or self._ring[0].shape[1] != width or self._ring[0].dtype != x_host.dtype:
+            self._ring = [torch.empty((self.chunk_rows, width), dtype=x_host.dtype, device=dev) for _ in range(self.RING)]
         main = torch.cuda.current_stream(dev)
         cs = self._copy_stream
         cs.wait_stream(main)
-        bufs, evs = [], []
         starts = list(range(0, n, self.chunk_rows))
-        for s in starts:
+        copied = [None] * len(starts)         # event: chunk i landed in ring[i % RING]
+        consumed = [None] * len(starts)       # event: the kernel that read chunk i has finished
+
+        def issue_copy(i):
+            if i >= len(starts):
+                return
+            if i >= self.RING:
+                cs.wait_event(consumed[i - self.RING])
+            s = starts[i]
+            rows = min(self.chunk_rows, n - s)
             with torch.cuda.stream(cs):
-                xb = x_host[s:s + self.chunk_rows].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            bufs.append(xb)
-            evs.append(ev)
-        for s, xb, ev in zip(starts, bufs, evs):
-            main.wait_event(ev)
-            xb.record_stream(main)
-            ids = self.tokenize_device(xb)
-            out[s:s + self.chunk_rows].copy_(ids, non_blocking=True)
+                self._ring[i % self.RING][:rows].copy_(x_host[s:s + rows], non_blocking=True)
+                copied[i] = torch.cuda.Event()
+                copied[i].record(cs)
+
+        for i in range(min(self.RING, len(starts))):
+            issue_copy(i)
+        for i, s in enumerate(starts):
+            rows = min(self.chunk_rows, n - s)
+            main.wait_event(copied[i])
+            ids = self.tokenize_device(self._ring[i % self.RING][:rows])
+            consumed[i] = torch.cuda.Event()
+            consumed[i].record(main)
+            out[s:s + rows].copy_(ids, non_blocking=True)
+            issue_copy(i + self.RING)
         main.synchronize()
         return out
 

@@ -200,6 +200,49 @@ def test_tokenizer_corpus_pass_vs_reference():
     assert out.sem_ids_fut.shape == (2, L + 1) and out.token_type_ids.shape == (2, 3 * (L + 1))
 
 
+@pytest.mark.parametrize("D,hidden", [(768, ()), (64, (128,)), (32, (512, 256, 128))])
+def test_module_api_routes_to_the_tensor_core_tokeniser(D, hidden):
+    """SemanticIdTokenizer.precompute_corpus_ids -> RqVae.tokenize must run the tcgen05 tokeniser (prepared
+    state cached across batches) for K = 256 models -- D = 768, D = 64 and the shipped D = 32 (zero-padded to 64) -- and return
+    the exact kernel's ids (modules/tokenizer/semids.py:76-125)."""
+    from rq_vae_recommender_b200 import ops
+    from rq_vae_recommender_b200.modules.tokenizer.semids import SemanticIdTokenizer
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    Din, K, L, N = 768, 256, 3, 5000
+    m, enc, dec, _ = build("ste", 0, Din=Din, D=D, hidden=hidden, K=K, L=L, seed=4000 + D)
+    x = I.unit_rows(4100 + D, N, Din)
+    with torch.no_grad():          # live codebooks: residual rows of the encoder output, like a k-means-initialised model
+        res = m.encode(dev(x))
+        for l, layer in enumerate(m.layers):
+            layer.embedding.weight.copy_(res[torch.randperm(N, generator=torch.Generator().manual_seed(l))[:K].cuda()])
+            res = res - layer.embedding.weight[ops.rq_tokenize(res, [layer.embedding.weight])[:, 0]]
+    tok = SemanticIdTokenizer(input_dim=Din, output_dim=D, hidden_dims=list(hidden), codebook_size=K, n_layers=L, n_cat_feats=0).cuda()
+    tok.rq_vae = m.eval()
+    tok.corpus_batch = 2048         # three batches (one ragged) -> one prepare, three tensor-core launches
+
+    class Items:
+        def __len__(self):
+            return N
+        def __getitem__(self, idx):
+            idx = torch.as_tensor(idx)
+            return SeqBatch(user_ids=-torch.ones_like(idx), ids=idx.unsqueeze(0), ids_fut=-torch.ones_like(idx),
+                            x=torch.from_numpy(x)[idx], x_fut=-torch.ones_like(idx), seq_mask=torch.ones_like(idx, dtype=bool))
+    calls, preps = ops.TC_CALLS, ops.TC_PREPARES
+    cached = host(tok.precompute_corpus_ids(Items()))
+    assert ops.TC_CALLS - calls == 3 and ops.TC_PREPARES - preps == 1, (ops.TC_CALLS - calls, ops.TC_PREPARES - preps)
+    with torch.no_grad():
+        z = m.encode(dev(x))
+        cbs = [layer.codebook() for layer in m.layers]
+        exact = host(ops.rq_tokenize(z, cbs))
+    assert_ids_match(cached[:, :L], exact, host(z), [host(c) for c in cbs], f"module-api/tc D={D}")
+    assert np.array_equal(cached[:, :L], host(m.tokenize(dev(x))))
+    # an optimiser step (in-place update) must invalidate the cached state
+    with torch.no_grad():
+        m.layers[0].embedding.weight.mul_(1.01)
+    m.tokenize(dev(x))
+    assert ops.TC_PREPARES - preps == 2
+
+
 def test_training_loop_like_train_rqvae():
     """The call sequence of train_rqvae.py:136-292 (k-means warm-up call, AdamW steps, eval, corpus ids + diversity
     stats) on synthetic item features: the loss must fall and the id statistics must be well formed."""

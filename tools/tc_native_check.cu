@@ -1,8 +1,7 @@
 // Python-free harness around the C ABI's tensor-core tokeniser (include/rqb200.h: rqb200_tokenize_tc_prepare / _run):
 // seeded synthetic unit-norm rows and live codebooks, one run whose ids go to a file, then `iters` event-timed runs.
-// The kernel variant is chosen by the library's environment switches (RQB200_TC_64, RQB200_TC_PAIR), which are read once
-// per process -- so variants are compared by running this binary once per setting and `cmp`-ing the id files:
-//   tools/bin/tc_native_check 65536 768 3 20 /tmp/a.ids;  RQB200_TC_64=1 tools/bin/tc_native_check 65536 768 3 20 /tmp/b.ids;  cmp /tmp/a.ids /tmp/b.ids
+// Two builds of the library (e.g. -DTX_R=96 vs the default tile shape) are compared by running this binary once per build
+// (RQB200_LIB=path/to/other.so) and `cmp`-ing the id files.
 // A fresh GPU box spends about a minute importing torch; this starts in milliseconds, which matters when GPU time is short.
 // build: nvcc -O2 -std=c++17 -o tools/bin/tc_native_check tools/tc_native_check.cu -ldl      (run from the repo root)
 #include <cuda_runtime.h>
@@ -32,7 +31,8 @@ int main(int argc, char** argv) {
   const int iters = argc > 4 ? atoi(argv[4]) : 20;
   const char* out = argc > 5 ? argv[5] : nullptr;
   const int K = 256;
-  void* lib = dlopen("rq_vae_recommender_b200/librqb200.so", RTLD_NOW);
+  const char* libpath = getenv("RQB200_LIB") ? getenv("RQB200_LIB") : "rq_vae_recommender_b200/librqb200.so";
+  void* lib = dlopen(libpath, RTLD_NOW);
   if (!lib) { printf("dlopen failed: %s\n", dlerror()); return 2; }
   auto state_bytes = (StateBytesFn)dlsym(lib, "rqb200_tokenize_tc_state_bytes");
   auto prepare = (PrepareFn)dlsym(lib, "rqb200_tokenize_tc_prepare");
@@ -95,15 +95,15 @@ int main(int argc, char** argv) {
   se = cudaDeviceSynchronize();
   if (se != cudaSuccess) { printf("timed runs: %s\n", cudaGetErrorString(se)); return 1; }
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
-  const char* v64 = getenv("RQB200_TC_64"); const char* vp = getenv("RQB200_TC_PAIR"); const char* vt = getenv("RQB200_TC_TMA"); const char* vg = getenv("RQB200_TC64_GROUPS"); const char* vf = getenv("RQB200_TC_FASTSCAN");
-  printf("B=%d D=%d L=%d TC_64=%s GROUPS=%s TC_PAIR=%s TC_TMA=%s FASTSCAN=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
-         B, D, L, v64 ? v64 : "-", vg ? vg : "-", vp ? vp : "-", vt ? vt : "-", vf ? vf : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
+  const char* vpf = getenv("RQB200_TC_PREFETCH");
+  printf("B=%d D=%d L=%d lib=%s PREFETCH=%s: ids out of range %ld, fnv %016llx, re-ranked rows %d cands %d many %d, %.4f ms/run (%d runs), %.1f M items/s\n",
+         B, D, L, libpath, vpf ? vpf : "-", bad, (unsigned long long)h, stats[0], stats[1], stats[2], ms / iters, iters,
          B / (ms / iters) * 1e-3);
   // RQB200_TC_TRACE=1: one more run with the event timeline of CTA 0 switched on (stats[3] = stats[4] = 1, >= 4096 ints; the
   // records are (tag << 56 | payload << 48 | clock) at ((long long*)(stats + 128))[role * 256 ...], see TC_EV in tc_common.cuh)
   const char* vtr = getenv("RQB200_TC_TRACE");
   if (vtr && vtr[0] == '1') {
-    int* dtr; CK(cudaMalloc(&dtr, 4096 * 4)); CK(cudaMemset(dtr, 0, 4096 * 4));
+    int* dtr; CK(cudaMalloc(&dtr, 4096 * 4)); CK(cudaMemset(dtr, 0, 4096 * 4));   // [0,128) counters | 4 x 256 events | 24 x 8 x 5 phase clocks
     const int on[2] = {1, 1};
     CK(cudaMemcpy(dtr + 3, on, 8, cudaMemcpyHostToDevice));
     if (run(dx, D, B, dstate, D, K, L, dids, dtr, nullptr)) { printf("traced run failed: %s\n", last_error()); return 1; }
@@ -136,9 +136,26 @@ int main(int argc, char** argv) {
     static const char* tag_name[4][6] = {
         {"", "level start (t_empty ok)", "a_full ok, chunk step", "level issued", "", ""},
         {"", "a_empty/x_full ok, chunk step", "chunk converted+arrived", "", "", ""},
-        {"", "t_full ok", "scan end", "merged / verdict out", "tmem released", "level done (re-rank, id out)"},
-        {"", "t_full ok", "scan end", "id received (partner) / merged (owner, GROUPS=2)", "tmem released", "level done (re-rank, id out)"}};
+        {"", "t_full ok", "scan end", "merged / verdict out (tcx: exchange complete)", "tmem released (tcx: level done, ids out)", "level done (re-rank, id out)"},
+        {"", "t_full ok", "scan end", "id received (tcx: exchange complete)", "tmem released (tcx: level done, ids out)", "level done (re-rank, id out)"}};
     printf("timeline of CTA 0 (cycles since first event; payload = tile_index*16 + level-or-step), %zu events\n", recs.size());
+    {   // rq_tcx_kernel: per-warp phase clocks of the epilogue (CTA 0): scan end, exchange complete, queue complete, re-rank done, all done
+      const long long* ph = reinterpret_cast<const long long*>(tr.data() + 2176);
+      if (ph[0]) {
+        printf("epilogue phases of CTA 0, cycles since the step's earliest scan end; per warp: scan_end  +x_full  +phase1/sync  +re-rank  +sync\n");
+        for (int g = 0; g < 24; ++g) {
+          long long t0 = 0;
+          for (int e = 0; e < 8; ++e) { const long long v = ph[(g * 8 + e) * 5]; if (v && (!t0 || v < t0)) t0 = v; }
+          if (!t0) break;
+          printf("step %2d:", g);
+          for (int e = 0; e < 8; ++e) {
+            const long long* q = ph + (g * 8 + e) * 5;
+            printf("  w%d %5lld %5lld %5lld %5lld %5lld |", e, q[0] - t0, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3]);
+          }
+          printf("\n");
+        }
+      }
+    }
     for (const Rec& q : recs) {
       const bool step = (q.role == 0 && q.tag == 2) || q.role == 1;
       if (step && (q.pay & 15) != 0 && (q.pay & 15) != (D / 64 - 1)) continue;      // chunk steps: first and last only
