@@ -11,6 +11,10 @@ own shard (items are independent: weak scaling, no data-path collective); the ti
   e2e       items/s through the public host API (pinned host rows -> H2D -> kernels -> D2H ids inside the timing)
   roofline  algorithmic HBM bytes of the dominant kernel / its event-timed duration vs MEASURED_PEAKS.json
   cpu_baseline  the torch-CPU port of the reference path (oracle/rq_oracle_torch.py) on this host's cores, bounded sample
+  prepare_ms    one-time cost of the frozen-codebook state (fp16 images, float64 Gram tables), outside the timed steps
+  c3            (N > 1) BASELINE config 3: an 84 000-item corpus sharded over the ranks: local tokenise + all-gather of the
+                int32 id blocks + all-reduce of the [L,K] usage counts per step, checked against one GPU tokenising the whole
+                corpus; plus one Lloyd iteration (assign + fp64 accumulate + all-reduce + update) at 20 000 x 32 and x 768
 
 --impl reference times that CPU port as the reference arm (the reference is pure Python/PyTorch: there is nothing
 to compile into oracle/_ref).
@@ -179,6 +183,87 @@ def run_reference(args):
     }))
 
 
+def run_c3(world, rank, cbs, torch, dist, ops, parallel):
+    """BASELINE.json config 3: ~84K items x 768 tokenised across the ranks with the collectives north_star names
+    (modules/tokenizer/semids.py:76-110 corpus pass, train_rqvae.py:285-289 usage counts, init/kmeans.py:39-70 Lloyd update)."""
+    import inputs as I
+    n3 = 84000
+    x_all = I.unit_rows(4321, n3, D)                       # same corpus on every rank (seeded), each keeps its shard
+    lo, hi = parallel.shard_bounds(n3, world, rank)
+    xs = torch.from_numpy(x_all[lo:hi]).cuda()
+    tok = parallel.CorpusTokenizer(cbs)
+
+    def step():
+        ids_local = tok.tokenize_device(xs)
+        table = parallel.all_gather_rows(ids_local.to(torch.int32), n3)
+        usage = parallel.codebook_usage(ids_local, K)
+        return table, usage
+
+    for _ in range(5):
+        table, usage = step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    steps = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        table, usage = step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms_rank = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    per_rank = [torch.zeros_like(ms_rank) for _ in range(world)]
+    dist.all_gather(per_rank, ms_rank)
+    per_rank = [float(t.item()) for t in per_rank]
+    # one GPU tokenising the whole corpus: the strong-scaling reference AND the parity check of the sharded table
+    out = {"items": n3, "steps": steps, "ms_per_step_per_rank": per_rank, "ms_per_step": max(per_rank),
+           "items_per_sec": n3 / (max(per_rank) * 1e-3),
+           "timed": "local tokenise + all_gather(int32 ids) + all_reduce([L,K] usage), eager launches, NCCL"}
+    match = torch.zeros(1, device="cuda")
+    if rank == 0:
+        xf = torch.from_numpy(x_all).cuda()
+        for _ in range(5):
+            full = tok.tokenize_device(xf)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            full = tok.tokenize_device(xf)
+        e1.record()
+        torch.cuda.synchronize()
+        out["single_gpu_ms"] = e0.elapsed_time(e1) / 50
+        out["speedup_vs_single_gpu"] = out["single_gpu_ms"] / out["ms_per_step"]
+        ok = bool(torch.equal(full.to(torch.int32), table)) and bool(torch.equal(ops.sid_histogram(full, K), usage))
+        match[0] = 1.0 if ok else 0.0
+        del xf
+    dist.broadcast(match, src=0)
+    out["sharded_ids_match_single"] = bool(match.item() == 1.0)
+    # one Lloyd iteration with its all-reduce (init/kmeans.py:39-58), shapes of train_rqvae.py:179-181
+    out["kmeans_lloyd_iteration_ms"] = {}
+    for dk in (32, D):
+        n_k = 20000
+        xk_all = I.unit_rows(99, n_k, dk)
+        klo, khi = parallel.shard_bounds(n_k, world, rank)
+        xk = torch.from_numpy(xk_all[klo:khi]).cuda()
+        cen = torch.from_numpy(xk_all[:K].copy()).cuda()
+        buf = ops.kmeans_workspace(xk, K)
+
+        def lloyd():
+            ops.kmeans_assign_accumulate(xk, cen, buf)
+            dist.all_reduce(buf["sums"]); dist.all_reduce(buf["counts"])
+            ops.kmeans_finalize(xk, cen, buf, None)
+
+        for _ in range(5):
+            lloyd()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            lloyd()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 50], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["kmeans_lloyd_iteration_ms"][f"20000x{dk}"] = float(t.item())
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +293,18 @@ def main():
     cbs = [torch.from_numpy(c).cuda() for c in cbs_h]
     use_tc = args.path == "tc" or (args.path == "auto" and ops.tc_supported(D, K, L))
     tok = parallel.CorpusTokenizer(cbs, use_tc=use_tc)
+    # one-time cost of the frozen-codebook state (not part of a step: the codebooks of a trained model do not change)
+    prepare_ms = None
+    if use_tc:
+        ops.TcState(cbs)
+        torch.cuda.synchronize()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        ops.TcState(cbs)
+        pe1.record()
+        torch.cuda.synchronize()
+        prepare_ms = pe0.elapsed_time(pe1)
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda") if use_tc else None
 
     def step():
         return tok.tokenize_device(x)
@@ -247,10 +344,21 @@ def main():
         n_after = len(clocks.rows)
     ops.LAUNCHES = l0 + launches_timed                  # gpu_launches counts the timed region only
     launches = ops.LAUNCHES - l0
+    rerank = None
+    if use_tc:                                          # re-rank rate of the deterministic margin (one extra untimed pass)
+        stats.zero_()
+        tok.tokenize_device(x, stats=stats)
+        st_h = stats.cpu().tolist()
+        rerank = {"rows_reranked": st_h[0], "candidates_rescored": st_h[1], "rows_with_3plus_candidates": st_h[2],
+                  "fraction_of_row_levels": st_h[0] / float(N_ITEMS * L)}
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     t = torch.tensor([total_ms], device="cuda")
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * N_ITEMS * args.steps / (total_ms * 1e-3)
@@ -279,6 +387,8 @@ def main():
     torch.cuda.synchronize()
     h2d_gbs = 3 * x_h.nbytes / (time.perf_counter() - t0) / 1e9
     del xd_tmp
+    c3 = run_c3(world, rank, cbs if rank == 0 else [torch.from_numpy(c).cuda() for c in make_problem(8192, seed=1234)[1]],
+                torch, dist, ops, parallel) if world > 1 else None
 
     if rank == 0:
         peaks = {}
@@ -294,7 +404,11 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_items": N_ITEMS,
-                       "kernel": "tcgen05 fp16 filter + exact fp32 re-rank" if use_tc else "fp32 CUDA-core fused chain",
+                       "kernel": ("rq_tcx_kernel: tcgen05 fp16 filter (deterministic margin) + exact fp32 re-rank" if use_tc
+                                  else "fp32 CUDA-core fused chain"),
+                       "api": "parallel.CorpusTokenizer -> ops.rq_tokenize_tc with a prepared state: the routing RqVae.tokenize / "
+                              "SemanticIdTokenizer.precompute_corpus_ids use (ops.rq_tokenize_auto)",
+                       "ms_per_step_per_rank": per_rank_ms,
                        "parallelism": f"items sharded over {world} GPU(s), no data-path collective",
                        "l2": "input batch (201 MB) exceeds the 126 MB L2; no flush between steps"},
             "clocks": dict(clocks.summary(), note=("sampled at 100 ms over pre-load + warm-up + timed region + 0.5 s "
@@ -305,11 +419,17 @@ def main():
                     "h2d_copy_gbs_measured": h2d_gbs,
                     "h2d_bound_items_per_sec": world * h2d_gbs * 1e9 / (4 * D)},
             "gpu_launches": launches,
+            "prepare_ms": prepare_ms,
+            "rerank": rerank,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": tok.measured_traffic_bytes(),
+                         "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full "
+                                           "capture of this kernel at this shape (profiles/r2_tcx_ncu_summary.csv), not measured in this run",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                          "kernel_ms": kern_ms, "algorithmic_bytes": algorithmic_bytes(N_ITEMS)},
         }
+        if c3 is not None:
+            out["c3"] = c3
         if world == 1 and not args.no_cpu_baseline:
             v, threads, sample = cpu_port_items_per_sec(x_h, cbs_h)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}

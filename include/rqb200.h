@@ -130,6 +130,22 @@ int rqb200_gemm_bf16(const void* a_image, const void* w_image, int M, int N, int
 int rqb200_sid_histogram(const int64_t* ids, int B, int L, int K, int64_t* hist /* [L,K], zeroed here */,
                          void* stream);
 
+/* Dedup column of the corpus table, modules/tokenizer/semids.py:94-108: rank[i] = number of rows j < i with the same id tuple
+ * (the reference's O(N^2) compare), and in the same pass the diversity statistics of train_rqvae.py:276-283:
+ * stats[0] = max rank (max_id_duplicates * N), stats[1] = number of distinct tuples, *entropy = -sum p log p over the distinct
+ * tuples.  Direct-table algorithm: needs K^L <= 2^26 (workspace_bytes returns 0 otherwise and the call RQB_ERR_UNSUPPORTED:
+ * the caller falls back to a sort).  ids [N,L] int64 row-major; ids outside [0,K) make a row its own group. */
+size_t rqb200_sid_dedup_workspace_bytes(int N, int L, int K);
+int rqb200_sid_dedup_rank(const int64_t* ids, int N, int L, int K, int64_t* rank /* [N] */, int* stats /* [2] */,
+                          double* entropy /* [1] */, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sequence tokenisation from the corpus table, semids.py:112-146 (`cached_ids[ids]`, -1 under the padding mask,
+ * token_type_ids): out[b, s*C + c] = seq_mask[b,s] ? cached_ids[item_ids[b,s], c] : -1; token_type[b, s*C + c] = c.
+ * seq_mask (bytes, 0 = padding) and token_type may be null; strides in elements. */
+int rqb200_sid_gather(const int64_t* cached_ids, int64_t n_corpus, int C, const int64_t* item_ids, int64_t item_stride,
+                      const unsigned char* seq_mask, int64_t mask_stride, int B, int S, int64_t* out /* [B, S*C] */,
+                      int64_t* token_type /* [B, S*C] or null */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ from typing import Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librqb200.so")
-SOURCES = ["api.cu", "rq_simt.cu", "dense.cu", "rq_tc.cu", "rq_tcx.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "rq_simt.cu", "dense.cu", "rq_tc.cu", "rq_tcx.cu", "rq_tcx96.cu", "gemm_tc.cu", "sid.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -58,6 +58,9 @@ _SIGNATURES = {
     "rqb200_l2norm_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     "rqb200_l2norm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     "rqb200_sid_histogram": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "rqb200_sid_dedup_workspace_bytes": (c_size, [c_int, c_int, c_int]),
+    "rqb200_sid_dedup_rank": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "rqb200_sid_gather": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "rqb200_bf16_image_bytes": (c_size, [c_int, c_int]),
     "rqb200_f32_to_bf16_image": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "rqb200_gemm_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),

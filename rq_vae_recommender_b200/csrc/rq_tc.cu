@@ -15,9 +15,15 @@
 #include "tc_common.cuh"
 
 // csrc/rq_tcx.cu: the transposed CTA-pair kernel (codes on the TMEM lanes); shares the prepared state
-int tcx_can_run(const float* x, int64_t ldx, int sm_count);
-int tcx_run(const float* x, int64_t ldx, int B, const void* state, int D, int L, int64_t* ids, int* stats, int sm_count,
-            bool trace, cudaStream_t st);
+// csrc/rq_tcx.cu / rq_tcx96.cu: the same kernel at two tile shapes (64 / 96 rows per CTA)
+int tcx_run_r64(const float* x, int64_t ldx, int B, const void* state, int D, int L, int64_t* ids, int* stats, int sm_count,
+                bool trace, cudaStream_t st);
+int tcx_run_r96(const float* x, int64_t ldx, int B, const void* state, int D, int L, int64_t* ids, int* stats, int sm_count,
+                bool trace, cudaStream_t st);
+// TMA needs a 16-byte aligned base and row pitch; the kernel runs as CTA pairs
+static int tcx_can_run(const float* x, int64_t ldx, int sm_count) {
+  return ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && sm_count >= 2;
+}
 
 extern "C" int rqb200_tokenize_tc_supported(int D, int K, int L) {
   return (K == TC_K && D >= TC_KC && D <= TC_MAX_D && D % TC_KC == 0 && L >= 1 && L <= RQB_MAX_LEVELS) ? 1 : 0;
@@ -224,5 +230,11 @@ extern "C" int rqb200_tokenize_tc_run(const float* x, int64_t ldx, int B, const 
                 "tokenize_tc_run: x must be 16-byte aligned with a row stride that is a multiple of 4 floats (and the device needs >= 2 SMs)");
   static const bool want_trace = []() { const char* e = getenv("RQB200_TC_TRACE"); return e && e[0] == '1'; }();
   const bool trace = want_trace && stats;       // tracing: the caller passes >= 4096 ints (tools/tc_native_check.cu)
-  return tcx_run(x, ldx, B, state, D, L, ids, stats, sm_count, trace, st);
+  // Tile shape: 96-row CTAs move a third fewer codebook bytes and hand-offs per row and win once every CTA pair has several
+  // tiles (12 101 rows: 0.041 vs 0.052 ms; 84 000: 0.193 vs 0.204); 64-row CTAs have the shorter pipeline and win below that
+  // (5 000 x 256: 0.053 vs 0.072 ms).  Both return identical ids (profiles/r2_tcx_shapes.txt).
+  static const int force = []() { const char* e = getenv("RQB200_TC_ROWS"); return e ? atoi(e) : 0; }();
+  const bool big = force ? force == 96 : (int64_t)B > 128ll * (sm_count / 2);     // more than one 64-row tile per CTA
+  return big ? tcx_run_r96(x, ldx, B, state, D, L, ids, stats, sm_count, trace, st)
+             : tcx_run_r64(x, ldx, B, state, D, L, ids, stats, sm_count, trace, st);
 }

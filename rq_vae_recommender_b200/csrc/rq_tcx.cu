@@ -38,32 +38,48 @@
 // 2-stage ring (measured: 9-12 K cycles per level instead of 4.6 K); with 64 rows (96 KB) there is room for 6 stages, four TMEM
 // accumulator buffers (the MMA stream runs up to three levels ahead of the scans), and 7 x 74 pair tiles cover 65 536 rows.
 #ifndef TX_R
-#define TX_R 64                                   // rows per CTA per tile (multiple of 32): 64 or 96
+#define TX_R 64                                   // rows per CTA per tile (multiple of 32): 64 here, 96 in rq_tcx96.cu (same source)
 #endif
+// The file is compiled twice (rq_tcx96.cu includes it with TX_R = 96): every symbol with linkage carries the tile shape.
+#define TX_CAT2(a, b) a##b
+#define TX_CAT(a, b) TX_CAT2(a, b)
+#define TX_SFX(name) TX_CAT(name, TX_CAT(_r, TX_R))
+#define rq_tcx_kernel TX_SFX(rq_tcx_kernel)
+#define tcx_run TX_SFX(tcx_run)
+#define TxSmem TX_SFX(TxSmem)
+#define TxParams TX_SFX(TxParams)
 #define TX_PR (2 * TX_R)                          // rows per pair tile = MMA N
 #define TX_NG (TX_R / 32)                         // 32-row scan groups per warp and level
 #define TX_SLOT_BYTES (TX_R * TC_KC * 2)          // one k-chunk of the fp16 image
 #if TX_R == 64
+// 64 rows: image 96 KB -> 4 codebook stages, 3 staging boxes of 16 KB, four TMEM buffers, everything double-buffered.  Best for
+// small and medium batches (short tiles, 7 x 74 pair tiles cover 65 536 rows).
 #define TX_NBX 2                                  // staging boxes per chunk pair: 32 rows x 128 floats = 16 KB
-#define TX_NB 4                                   // codebook ring stages (16 KB)
+#define TX_NB_MAX 4                               // codebook ring stages (16 KB)
+#define TX_NX 3                                   // x staging ring stages
 #define TX_NT 4                                   // TMEM accumulator buffers of TX_PR columns
 #define TX_XBUF 2                                 // exchange buffers: 2 = the level-0 scan of a tile overlaps the previous tile's last finalise
+#define TX_RIBUF 2                                // row-statistics buffers
 #else
+// 96 rows: image 144 KB.  Two thirds of the codebook bytes and of the per-level hand-offs per row, but shared memory is tight:
+// 3 codebook stages only when the id bytes of L <= 4 levels fit (else 2), 2 staging boxes of 12 KB, everything single-buffered.
+// Best for large batches (5 x 74 pair tiles cover 65 536 rows).
 #define TX_NBX 4                                  // 24 rows x 128 floats = 12 KB
-#define TX_NB 2
+#define TX_NB_MAX 3
+#define TX_NX 2
 #define TX_NT 2
 #define TX_XBUF 1
+#define TX_RIBUF 1
 #endif
 #define TX_XBOX_ROWS (TX_R / TX_NBX)              // fp32 staging box rows.  512-byte box rows on purpose: with 128-byte rows the TMA
 #define TX_XBOX_COLS 128                          // engine delivered 13 B/clk/SM (profiles/r2_tcx_bringup.txt)
 #define TX_XBOX_BYTES (TX_XBOX_ROWS * TX_XBOX_COLS * 4)
 #define TX_RPW (TX_XBOX_ROWS / TC_NCONV_WARPS)    // box rows per converter warp
-#define TX_NX 3                                   // x staging ring stages
 #define TX_ROWS_PER_FIN (TX_R / TC_NEPI_WARPS)    // rows a warp finalises per level
 
 struct TxSmem {
   uint64_t a_full[TC_MAX_KC], a_empty[TC_MAX_KC];
-  uint64_t b_full[TX_NB], b_empty[TX_NB];
+  uint64_t b_full[TX_NB_MAX], b_empty[TX_NB_MAX];
   uint64_t xs_full[TX_NX], xs_empty[TX_NX];
   uint64_t t_full[TX_NT], t_empty[TX_NT];
   uint64_t x_full[TX_XBUF];               // [step parity] (min, mask) of every (row of this CTA, warp slot) delivered: 4 local + 4 remote warps.
@@ -74,8 +90,7 @@ struct TxSmem {
   uint32_t tmem_base;
   uint32_t fl_count, fl_next;       // queue of rows that need the exact re-rank
   uint32_t tiles_done;              // += 1 per epilogue warp of EITHER CTA per finished tile (monotonic: guards rowinfo[] reuse)
-  uint32_t rowinfo[2][TX_PR];       // [tile parity][pair row]: bf16_up(||fp16(x)-x||^2) << 16 | bf16_up(||x||^2)
-  alignas(16) unsigned char ids8[RQB_MAX_LEVELS][TX_PR];   // [level][pair row]: ids of the current tile (level-major: one uniform byte load per table and row)
+  uint32_t rowinfo[TX_RIBUF][TX_PR];  // [tile % TX_RIBUF][pair row]: bf16_up(||fp16(x)-x||^2) << 16 | bf16_up(||x||^2)
   unsigned char flist[TX_R];
   alignas(16) uint2 exch[TX_XBUF][8][TX_R];           // [step parity][warp slot = 4 * source CTA + lane quarter][row of this CTA] = (min as float bits, candidate mask)
   alignas(16) uint2 xstage[TX_XBUF][4][TX_R];         // [step parity] what this CTA's warps found for the PEER's rows: one 768-byte DSMEM bulk copy per warp and level
@@ -180,6 +195,7 @@ struct TxParams {
   int64_t* ids;         // [B][L]
   int* stats;           // optional: [0] rows re-ranked, [1] candidates re-scored, [2] rows with >= 3 candidates
   int prefetch;         // 1: the x producer pulls the next tile's rows into L2 while this tile is staged
+  int nb;               // codebook ring stages in use (<= TX_NB_MAX)
 };
 
 template <bool kTrace>
@@ -187,8 +203,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* sX = tsm;                                          // [TC_MAX_KC][12 KB] fp16 image of this CTA's rows
   unsigned char* sC = sX + TC_MAX_KC * TX_SLOT_BYTES;               // [TX_NB][16 KB] codebook ring
-  unsigned char* sS = sC + TX_NB * TC_BSTAGE_BYTES;                 // [TX_NX][12 KB] fp32 staging ring
+  unsigned char* sS = sC + p.nb * TC_BSTAGE_BYTES;                  // [TX_NX] fp32 staging ring
   TxSmem* ms = reinterpret_cast<TxSmem*>(sS + TX_NX * TX_XBOX_BYTES);
+  // ids of the current tile, level-major bytes [L][TX_PR] behind the fixed part (sized by L at launch: at TX_R = 96 the third
+  // codebook stage only fits with <= 4 levels of them)
+  unsigned char* const ids8 = reinterpret_cast<unsigned char*>(ms + 1);
+  const uint32_t nb = (uint32_t)p.nb;                                 // codebook ring depth (run time: see tcx_run)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkc = p.nkc, L = p.L;
@@ -199,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
   if (tid == 0) {
     if ((smem_u32(tsm) & 1023u) != 0) __trap();                      // the swizzle pattern needs a 1024-byte aligned base
     for (int i = 0; i < TC_MAX_KC; ++i) { mbar_init(&ms->a_full[i], 2 * TX_NBX * TC_NCONV_WARPS); mbar_init(&ms->a_empty[i], 1); }
-    for (int i = 0; i < TX_NB; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
+    for (int i = 0; i < TX_NB_MAX; ++i) { mbar_init(&ms->b_full[i], 1); mbar_init(&ms->b_empty[i], 1); }
     for (int i = 0; i < TX_NX; ++i) { mbar_init(&ms->xs_full[i], 1); mbar_init(&ms->xs_empty[i], TC_NCONV_WARPS); }
     for (int i = 0; i < TX_NT; ++i) { mbar_init(&ms->t_full[i], 1); mbar_init(&ms->t_empty[i], 2 * TC_NEPI_WARPS); }
     for (int i = 0; i < TX_XBUF; ++i) mbar_init(&ms->x_full[i], TC_NEPI_WARPS);
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
       for (int unit = u_first; unit < u_count; unit += u_step)
         for (int l = 0; l < L; ++l)
           for (int kc = 0; kc < nkc; ++kc, ++s) {
-            const uint32_t st = s % TX_NB, u = s / TX_NB;
+            const uint32_t st = s % nb, u = s / nb;
             tx_wait(&ms->b_empty[st], (u & 1) ^ 1);     // local: the leader's commits are multicast
             if (tc_elect_one()) {
               if (crank == 0) mbar_expect_tx(&ms->b_full[st], 2 * TC_BSTAGE_BYTES);
@@ -251,8 +271,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
               tx_wait(&ms->a_full[kc], it & 1);
               TC_EV(0, 2, it * 16 + kc);
             }
-            const uint32_t st = s % TX_NB;
-            tx_wait(&ms->b_full[st], (s / TX_NB) & 1);
+            const uint32_t st = s % nb;
+            tx_wait(&ms->b_full[st], (s / nb) & 1);
             tc_fence_after();
             const uint64_t adesc = tc_smem_desc(c_base + st * TC_BSTAGE_BYTES);      // M side: codes
             const uint64_t bdesc = tc_smem_desc(x_base + kc * TX_SLOT_BYTES);        // N side: rows
@@ -348,10 +368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
           }
           if (pr == npair - 1 && bx == TX_NBX - 1) {
             // row statistics of the tile -> both CTAs (the scan of either CTA needs the margin of all 192 rows).  The buffer of
-            // this parity was last read by the epilogue of tile it - 2 (both CTAs): wait until all 16 warps have left that tile.
-            if (it >= 2) {
+            // this index was last read by the epilogue of tile it - TX_RIBUF (both CTAs): wait until all 16 warps have left that tile.
+            if (it >= TX_RIBUF) {
               const long long t0 = clock64();
-              while (*reinterpret_cast<volatile uint32_t*>(&ms->tiles_done) < 2u * TC_NEPI_WARPS * (it - 1)) {
+              while (*reinterpret_cast<volatile uint32_t*>(&ms->tiles_done) < 2u * TC_NEPI_WARPS * (it - TX_RIBUF + 1)) {
                 __nanosleep(200);
                 if (clock64() - t0 > 4000000000LL) __trap();
               }
@@ -368,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
               const float ss = tx_transpose_sum(vs, lane), ee = tx_transpose_sum(ve, lane);
               if (lane < TX_NBX * TX_RPW) {
                 const uint32_t ri = (tc_bf16_up(ee) << 16) | tc_bf16_up(ss);
-                const uint32_t idx = (it & 1) * TX_PR + crank * TX_R + (uint32_t)((lane / TX_RPW) * TX_XBOX_ROWS + cw * TX_RPW + lane % TX_RPW);
+                const uint32_t idx = (it % TX_RIBUF) * TX_PR + crank * TX_R + (uint32_t)((lane / TX_RPW) * TX_XBOX_ROWS + cw * TX_RPW + lane % TX_RPW);
                 (&ms->rowinfo[0][0])[idx] = ri;
                 tx_st_async_b32(peer_ri + idx * 4u, ri, peer_rifull0 + (it & 1) * 8u);
               }
@@ -403,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
     const uint32_t xout_pstride = own ? 8u * TX_R : 4u * TX_R;
     const uint32_t exch_peer0 = cluster_map(smem_u32(&ms->exch[0][slot][0]), crank ^ 1u);
     const uint32_t xfull_dst0 = cluster_map(smem_u32(&ms->x_full[0]), (uint32_t)ch);
-    const uint32_t ids_peer = cluster_map(smem_u32(&ms->ids8[0][0]), crank ^ 1u);
+    const uint32_t ids_peer = cluster_map(smem_u32(ids8), crank ^ 1u);
     const uint32_t idsrdy_peer = cluster_map(smem_u32(&ms->ids_ready), crank ^ 1u);
     const uint32_t tempty_leader = cluster_map(smem_u32(&ms->t_empty[0]), 0);
     const bool designated = (e == 4 * (int)crank);       // scans this CTA's own rows (ch == crank): see the queue reset below
@@ -432,9 +452,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
         const uint32_t xfull_dst = xfull_dst0 + xb * 8u;
         if (l == 0) {
           tx_wait(&ms->ri_full[it & 1], (it >> 1) & 1);                       // row statistics of this tile (both CTAs' rows)
-          ri0 = ms->rowinfo[it & 1][ch * TX_R + lane];
-          ri1 = ms->rowinfo[it & 1][ch * TX_R + 32 + lane];
-          if (TX_NG > 2) ri2 = ms->rowinfo[it & 1][ch * TX_R + 64 + lane];
+          ri0 = ms->rowinfo[it % TX_RIBUF][ch * TX_R + lane];
+          ri1 = ms->rowinfo[it % TX_RIBUF][ch * TX_R + 32 + lane];
+          if (TX_NG > 2) ri2 = ms->rowinfo[it % TX_RIBUF][ch * TX_R + 64 + lane];
         }
         const float mg0 = tx_margin(lc, ri0), mg1 = tx_margin(lc, ri1), mg2 = tx_margin(lc, ri2);
         tx_wait(&ms->t_full[buf], u & 1);
@@ -452,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
 #pragma unroll 1
           for (int g3 = 0; g3 < TX_NG; ++g3) {
             const float mgg = g3 == 0 ? mg0 : (g3 == 1 ? mg1 : mg2);         // margin of row 32 g3 + lane
-            const unsigned char* idrow = &ms->ids8[0][ch * TX_R + g3 * 32];
+            const unsigned char* idrow = ids8 + ch * TX_R + g3 * 32;
             float h[32];
             if constexpr (NT == 0) {
               tc_ld_wait();
@@ -514,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
           const int prow = (int)crank * TX_R + frow;
           const int grow = (unit * 2 + (int)crank) * TX_R + frow;      // global row
           if (lane < TX_ROWS_PER_FIN) {
-            const float mgf = tx_margin(lc, ms->rowinfo[it & 1][prow]);
+            const float mgf = tx_margin(lc, ms->rowinfo[it % TX_RIBUF][prow]);
             uint32_t mw[8], kw[8];
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -535,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
             const int my_id = first < 0 ? 0 : first;
             if ((cnt != 1) && grow < p.B) ms->flist[atomicAdd(&ms->fl_count, 1u)] = (unsigned char)frow;
             else {
-              ms->ids8[l][prow] = (unsigned char)my_id;
+              ids8[l * TX_PR + prow] = (unsigned char)my_id;
               if (grow < p.B) p.ids[(int64_t)grow * L + l] = my_id;
             }
           }
@@ -565,7 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
             const int rprow = (int)crank * TX_R + rrow;
             const int rgrow = (unit * 2 + (int)crank) * TX_R + rrow;
             // candidate words of the row (lane w < 8 holds word w); a warp whose minimum is outside the margin contributes nothing
-            const float mgf = tx_margin(lc, ms->rowinfo[it & 1][rprow]);
+            const float mgf = tx_margin(lc, ms->rowinfo[it % TX_RIBUF][rprow]);
             const uint2 ex = ms->exch[xb][lane & 7][rrow];
             float M = __uint_as_float(ex.x);
 #pragma unroll
@@ -590,13 +610,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
             int ka = next_cand(), kb = next_cand();
             float4 res[6], va[6], vb[6];                                 // three row buffers: a fourth one spills (no L1: a spill is an L2 trip)
             ld_row(p.x + (int64_t)rgrow * p.ldx, res);
-            if (l > 0) ld_row(p.cbf + ((size_t)0 * TC_K + (size_t)ms->ids8[0][rprow]) * D, vb);     // first prior code travels in vb
+            if (l > 0) ld_row(p.cbf + ((size_t)0 * TC_K + (size_t)ids8[rprow]) * D, vb);     // first prior code travels in vb
             if (ka >= 0) ld_row(cl + (size_t)ka * D, va);
 #pragma unroll 1
             for (int j = 0; j < l; ++j) {
 #pragma unroll
               for (int i = 0; i < 6; ++i) { res[i].x -= vb[i].x; res[i].y -= vb[i].y; res[i].z -= vb[i].z; res[i].w -= vb[i].w; }   // rqvae.py:130, level order
-              if (j + 1 < l) ld_row(p.cbf + ((size_t)(j + 1) * TC_K + (size_t)ms->ids8[j + 1][rprow]) * D, vb);
+              if (j + 1 < l) ld_row(p.cbf + ((size_t)(j + 1) * TC_K + (size_t)ids8[(j + 1) * TX_PR + rprow]) * D, vb);
             }
             if (kb >= 0) ld_row(cl + (size_t)kb * D, vb);                // level 0: requested together with x and the first candidate
             float cca = (ka >= 0) ? __ldg(ccl + ka) : 0.f, ccb = (kb >= 0) ? __ldg(ccl + kb) : 0.f;   // in flight with the rows
@@ -642,7 +662,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
             }
             if (besti > 255) besti = firsti < 0 ? 0 : firsti;          // all-NaN distances: keep a valid code
             if (lane == 0) {
-              ms->ids8[l][rprow] = (unsigned char)besti;
+              ids8[l * TX_PR + rprow] = (unsigned char)besti;
               p.ids[(int64_t)rgrow * L + l] = besti;
             }
             ++n_rows; n_cand += nc; n_many += (nc >= 3);
@@ -668,7 +688,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rq_tcx_kernel(const __grid_cons
           // CTA's rows: ch == crank) -- after this reset in program order
           ms->fl_count = 0; ms->fl_next = 0;
           fence_proxy_async();
-          tx_bulk_s2peer(ids_peer + (uint32_t)(l * TX_PR) + crank * TX_R, &ms->ids8[l][crank * TX_R], TX_R, idsrdy_peer);
+          tx_bulk_s2peer(ids_peer + (uint32_t)(l * TX_PR) + crank * TX_R, ids8 + l * TX_PR + crank * TX_R, TX_R, idsrdy_peer);
           mbar_expect_tx(&ms->ids_ready, TX_R);
         }
         if (l == L - 1) {
@@ -712,11 +732,6 @@ static int tx_launch(const TxParams& p, int grid, size_t smem, cudaStream_t st) 
   return RQB_OK;
 }
 
-// 1 when rqb200_tokenize_tc_run can take this x on the transposed kernel (TMA needs a 16-byte aligned base and row pitch)
-int tcx_can_run(const float* x, int64_t ldx, int sm_count) {
-  return ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && sm_count >= 2;
-}
-
 int tcx_run(const float* x, int64_t ldx, int B, const void* state, int D, int L, int64_t* ids, int* stats, int sm_count,
             bool trace, cudaStream_t st) {
   const char* base = reinterpret_cast<const char*>(state);
@@ -738,6 +753,12 @@ int tcx_run(const float* x, int64_t ldx, int B, const void* state, int D, int L,
   rc = tc_encode_2d(&p.tmapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, (uint64_t)D, (uint64_t)B, (uint64_t)ldx * 4, TX_XBOX_COLS, TX_XBOX_ROWS);
   if (rc) return rc;
   const int nclusters = p.ntiles < sm_count / 2 ? p.ntiles : sm_count / 2;
-  const size_t smem = (size_t)TC_MAX_KC * TX_SLOT_BYTES + TX_NB * TC_BSTAGE_BYTES + TX_NX * TX_XBOX_BYTES + sizeof(TxSmem);
+  // shared memory: image + codebook ring + staging ring + fixed part + id bytes of L levels; the ring gets as many 16 KB stages
+  // (<= TX_NB_MAX) as fit under the 227 KB limit
+  const size_t fixed = (size_t)TC_MAX_KC * TX_SLOT_BYTES + TX_NX * TX_XBOX_BYTES + sizeof(TxSmem) + (size_t)rqb_round_up((int64_t)L * TX_PR, 16);
+  int nbs = TX_NB_MAX;
+  while (nbs > 2 && fixed + (size_t)nbs * TC_BSTAGE_BYTES > 232448) --nbs;
+  p.nb = nbs;
+  const size_t smem = fixed + (size_t)nbs * TC_BSTAGE_BYTES;
   return trace ? tx_launch<true>(p, 2 * nclusters, smem, st) : tx_launch<false>(p, 2 * nclusters, smem, st);
 }

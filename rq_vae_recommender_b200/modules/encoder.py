@@ -53,6 +53,7 @@ class MLP(nn.Module):
             object.__setattr__(self, "_wimg_cache", cache)
         return cache[1]
 
+    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
     def forward(self, x: Tensor) -> Tensor:
         assert x.shape[-1] == self.input_dim, f"Invalid input dim: Expected {self.input_dim}, found {x.shape[-1]}"
         if self._bf16_wanted(x):

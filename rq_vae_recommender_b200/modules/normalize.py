@@ -1,4 +1,5 @@
 """modules/normalize.py of the reference (:6-17) on the l2norm kernels of csrc/dense.cu."""
+import torch
 from torch import nn
 from torch import Tensor
 
@@ -18,5 +19,6 @@ class L2NormalizationLayer(nn.Module):
         self.dim = dim
         self.eps = eps
 
+    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
     def forward(self, x) -> Tensor:
         return l2norm(x, dim=self.dim, eps=self.eps)

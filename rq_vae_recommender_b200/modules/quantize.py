@@ -132,6 +132,7 @@ class Quantize(nn.Module):
             return _KERNEL_MODE[self.forward_mode]
         raise Exception("Unsupported Quantize forward mode.")
 
+    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
     def forward(self, x, temperature) -> QuantizeOutput:
         assert x.shape[-1] == self.embed_dim
 

@@ -45,15 +45,21 @@ class RqVaeComputedLosses(NamedTuple):
 
 
 def count_unique_id_tuples(sem_ids: Tensor, codebook_size: int) -> Tensor:
-    """#distinct rows of a [B,L] id table.  Equals the reference's [B,B,L] triangular compare
-    (rqvae.py:159-167: rows with no later duplicate) without the O(B^2) memory."""
+    """#distinct rows of a [B,L] id table as a 0-d DEVICE tensor (no host sync in the training step).  Equals the reference's
+    [B,B,L] triangular compare (rqvae.py:159-167: rows with no later duplicate) without the O(B^2) memory: the direct-table
+    dedup kernel counts the groups (ops.sid_dedup_rank); key spaces beyond 2^26 sort the packed keys on the device."""
+    if sem_ids.is_cuda:
+        res = ops.sid_dedup_rank(sem_ids, codebook_size)
+        if res is not None:
+            return res[1]["n_unique"]
     L = sem_ids.shape[1]
     if codebook_size ** L < 2 ** 62:
         key = sem_ids[:, 0].clone()
         for l in range(1, L):
             key = key * codebook_size + sem_ids[:, l]
-        return torch.unique(key).numel()
-    return torch.unique(sem_ids, dim=0).shape[0]
+        skey = torch.sort(key).values
+        return (skey[1:] != skey[:-1]).sum() + 1 if len(skey) else torch.zeros((), dtype=torch.int64, device=sem_ids.device)
+    return torch.as_tensor(torch.unique(sem_ids, dim=0).shape[0], device=sem_ids.device)
 
 
 class RqVae(nn.Module, PyTorchModelHubMixin):
@@ -146,6 +152,7 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
         return (not pending_init and len(modes) == 1 and ops.MODE_GUMBEL not in modes and len(betas) == 1
                 and len(self.layers) <= 8)
 
+    @torch.compiler.disable      # librqb200 is called through ctypes: opaque to Dynamo (a compiled caller breaks the graph HERE, cleanly)
     def _chain(self, res: Tensor, gumbel_t: float, lean: bool):
         if self._fusable():
             mode = self.layers[0].kernel_mode()
@@ -180,6 +187,7 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
             quantize_loss=quantize_loss,
         )
 
+    @torch.compiler.disable
     @torch.no_grad()
     def tokenize(self, x: Tensor, mlp_precision: str = None) -> Tensor:
         """sem_ids [B,L] only: what SemanticIdTokenizer consumes (semids.py:125).  Large batches go through the tcgen05
@@ -214,9 +222,7 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
 
         with torch.no_grad():
             # Compute debug ID statistics
-            p_unique_ids = torch.as_tensor(
-                count_unique_id_tuples(sem_ids, self.codebook_size) / sem_ids.shape[0],
-                dtype=torch.float32, device=sem_ids.device)
+            p_unique_ids = (count_unique_id_tuples(sem_ids, self.codebook_size) / sem_ids.shape[0]).to(torch.float32)
 
         return RqVaeComputedLosses(
             loss=loss,

@@ -30,6 +30,10 @@ def dedup_rank(sem_ids: Tensor, codebook_size: int) -> Tensor:
     N, L = sem_ids.shape
     if N == 0:
         return torch.zeros(0, dtype=torch.int64, device=sem_ids.device)
+    if sem_ids.is_cuda:
+        res = ops.sid_dedup_rank(sem_ids, codebook_size)       # direct-table kernel: no sort, O(N) on near-unique tables
+        if res is not None:
+            return res[0]
     if codebook_size ** L < 2 ** 62:
         key = sem_ids[:, 0].clone()
         for l in range(1, L):
@@ -44,6 +48,29 @@ def dedup_rank(sem_ids: Tensor, codebook_size: int) -> Tensor:
     rank = torch.empty(N, dtype=torch.int64, device=key.device)
     rank[order] = pos - start
     return rank
+
+
+def corpus_id_stats(cached_ids: Tensor, codebook_size: int) -> dict:
+    """The ID-diversity numbers train_rqvae.py:276-292 logs after ``precompute_corpus_ids`` -- ``max_id_duplicates``,
+    ``rqvae_entropy`` and ``codebook_usage_{l}`` -- as 0-d device tensors from three kernel launches (dedup/entropy pass +
+    per-level usage histogram) instead of ``torch.unique(dim=0)`` + a Python loop over levels."""
+    n = cached_ids.shape[0]
+    sem_ids = cached_ids[:, :-1].contiguous()
+    L = sem_ids.shape[1]
+    out = {}
+    res = ops.sid_dedup_rank(sem_ids, codebook_size) if cached_ids.is_cuda else None
+    if res is not None:
+        _, st = res
+        out["rqvae_entropy"] = st["entropy"].to(torch.float32)
+    else:
+        _, counts = torch.unique(sem_ids, dim=0, return_counts=True)
+        p = counts / n
+        out["rqvae_entropy"] = -(p * torch.log(p)).sum()
+    out["max_id_duplicates"] = cached_ids[:, -1].max() / n
+    hist = ops.sid_histogram(sem_ids, codebook_size)
+    for l in range(L):
+        out[f"codebook_usage_{l}"] = (hist[l] > 0).sum() / codebook_size
+    return out
 
 
 class SemanticIdTokenizer(nn.Module):
@@ -117,8 +144,7 @@ class SemanticIdTokenizer(nn.Module):
         return self.cached_ids
 
     def _tokenize_seq_batch_from_cached(self, ids: Tensor) -> Tensor:
-        n = ids.shape[1]
-        return self.cached_ids[ids.flatten(), :].reshape(ids.shape[0], n * self.cached_ids.shape[1])
+        return ops.sid_gather(self.cached_ids, ids, None, want_token_type=False)[0]
 
     @torch.no_grad
     @eval_mode
@@ -131,14 +157,15 @@ class SemanticIdTokenizer(nn.Module):
         else:
             B, N = batch.ids.shape
             _, D = self.cached_ids.shape
-            sem_ids = self._tokenize_seq_batch_from_cached(batch.ids)
+            # one kernel: gather + -1 under the padding mask + token_type_ids (reference: index, repeat_interleave, masked
+            # assignment, arange().repeat())
+            sem_ids, token_type_ids = ops.sid_gather(self.cached_ids, batch.ids, batch.seq_mask)
             seq_mask = batch.seq_mask.repeat_interleave(D, dim=1)
-            sem_ids[~seq_mask] = -1
+            sem_ids_fut, token_type_ids_fut = ops.sid_gather(self.cached_ids, batch.ids_fut, None)
 
-            sem_ids_fut = self._tokenize_seq_batch_from_cached(batch.ids_fut)
-
-        token_type_ids = torch.arange(D, device=sem_ids.device).repeat(B, N)
-        token_type_ids_fut = torch.arange(D, device=sem_ids.device).repeat(B, 1)
+        if seq_mask is None:
+            token_type_ids = torch.arange(D, device=sem_ids.device).repeat(B, N)
+            token_type_ids_fut = torch.arange(D, device=sem_ids.device).repeat(B, 1)
         return TokenizedSeqBatch(
             user_ids=batch.user_ids,
             sem_ids=sem_ids,

@@ -395,6 +395,54 @@ def sid_histogram(ids: torch.Tensor, K: int) -> torch.Tensor:
     return hist
 
 
+def sid_dedup_rank(ids: torch.Tensor, K: int):
+    """Dedup column + diversity statistics of a corpus id table (semids.py:94-108, train_rqvae.py:276-283) in two launches.
+    Returns (rank [N] int64, stats) with stats = dict(max_rank, n_unique: 0-d int32 tensors, entropy: 0-d float64 tensor), all on
+    the device (no host sync), or None when the key space K^L is too large for the direct table (the caller sorts instead)."""
+    _need_cuda(ids)
+    lib = _lib.load()
+    ids = ids.contiguous()
+    N, L = ids.shape
+    ws_bytes = lib.rqb200_sid_dedup_workspace_bytes(N, L, K)
+    if ws_bytes == 0:
+        return None
+    dev = ids.device
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rank = torch.empty(N, dtype=torch.int64, device=dev)
+    stats = torch.empty(2, dtype=torch.int32, device=dev)
+    entropy = torch.empty(1, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.rqb200_sid_dedup_rank(_p(ids), N, L, K, _p(rank), _p(stats), _p(entropy), _p(ws), ws_bytes, _stream()),
+                   "sid_dedup_rank")
+    _count(2)
+    return rank, dict(max_rank=stats[0], n_unique=stats[1], entropy=entropy[0])
+
+
+def sid_gather(cached_ids: torch.Tensor, item_ids: torch.Tensor, seq_mask: Optional[torch.Tensor] = None,
+               want_token_type: bool = True):
+    """cached_ids[item_ids] -> [B, S*C] with -1 under the padding mask, and token_type_ids (semids.py:112-146), one launch."""
+    _need_cuda(cached_ids, item_ids)
+    lib = _lib.load()
+    cached_ids = cached_ids.contiguous()
+    if item_ids.stride(-1) != 1:
+        item_ids = item_ids.contiguous()
+    B, S = item_ids.shape
+    C = cached_ids.shape[1]
+    dev = cached_ids.device
+    out = torch.empty((B, S * C), dtype=torch.int64, device=dev)
+    tt = torch.empty((B, S * C), dtype=torch.int64, device=dev) if want_token_type else None
+    m = None
+    if seq_mask is not None:
+        m = seq_mask.to(torch.uint8) if seq_mask.dtype != torch.uint8 else seq_mask
+        if m.stride(-1) != 1:
+            m = m.contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rqb200_sid_gather(_p(cached_ids), cached_ids.shape[0], C, _p(item_ids), item_ids.stride(0), _p(m),
+                                         m.stride(0) if m is not None else 0, B, S, _p(out), _p(tt), _stream()), "sid_gather")
+    _count(1)
+    return out, tt
+
+
 # ---------------------------------------------------------------------------------------------- tensor-core tokeniser
 def tc_supported(D: int, K: int, L: int) -> bool:
     return bool(_lib.load().rqb200_tokenize_tc_supported(D, K, L))

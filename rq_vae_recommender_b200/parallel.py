@@ -121,14 +121,14 @@ class CorpusTokenizer:
 
     def measured_traffic_bytes(self):
         """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the 65 536 x 768 bench shape,
-        from the committed `ncu --set full` capture of the shipped kernel (profiles/r1_tc_final_summary.csv); None when no
+        from the committed `ncu --set full` capture of the shipped kernel (profiles/r2_tcx_ncu_summary.csv); None when no
         capture covers the active kernel."""
         import csv
         import os
         if not self.use_tc:
             return None
         path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
-                            "r1_tc_final_summary.csv")
+                            "r2_tcx_ncu_summary.csv")
         try:
             rows = list(csv.reader(open(path)))
             hdr, units, vals = rows[0], rows[1], rows[2]
@@ -175,13 +175,24 @@ def _default_finalize(x, centroids, buf, reseed):
 
 @torch.no_grad()
 def sharded_kmeans(x_local: torch.Tensor, k: int, n_total: int, group=None, max_iters: Optional[int] = None,
-                   stop_threshold: float = 1e-10, assign_accumulate=None, finalize=None, make_buf=None):
+                   stop_threshold: float = 1e-10, assign_accumulate=None, finalize=None, make_buf=None,
+                   check_every: int = 4):
     """init/kmeans.py semantics over a row-sharded x (every rank holds shard_bounds(n_total, world, rank)).
 
-    RNG: every rank draws the SAME global ``np.random.choice(n_total, k)`` (seed numpy identically on all ranks,
-    as for a single process) and, for empty clusters, rank 0 draws ``torch.randint(0, n_total)`` and broadcasts.
-    Rows named by a global index are fetched from their owner with a sum all-reduce of a one-hot-masked [k,D]
-    buffer.  Returns (centroids [k,D], local assignment, n_iters)."""
+    Per Lloyd iteration: local assign + fp64 accumulate (one kernel), the [k, D] fp64 sums and the [k] int32 counts are
+    all-reduced IN PLACE (two NCCL calls on the kernel's own buffers, no staging copy), identical centroid update on every
+    rank.  The host is consulted once every ``check_every`` iterations, not twice per iteration: the per-iteration shift and
+    an "a cluster came up empty" flag are recorded on the device.  Empty clusters are rare (every initial centroid is a data
+    row) and need the reference's host RNG draw in THAT iteration (kmeans.py:48-54), so a window that saw one is rolled back to
+    its snapshot and replayed with per-iteration host checks -- results are those of the reference's loop either way.  A window
+    may run up to ``check_every - 1`` iterations past convergence; with the reference's threshold (1e-10: a fixed point) they
+    change nothing.
+
+    RNG: every rank draws the SAME global ``np.random.choice(n_total, k)`` (seed numpy identically on all ranks, as for a
+    single process) and, for empty clusters, rank 0 draws ``torch.randint(0, n_total)`` and broadcasts.  Rows named by a
+    global index are fetched from their owners with ONE sum all-reduce of a one-hot-masked [k, D] buffer (init and re-seed
+    only; k rows with k different owners: a single small collective beats k broadcasts).
+    Returns (centroids [k,D], local assignment, n_iters)."""
     import torch.distributed as dist
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     world = dist.get_world_size(group) if distributed else 1
@@ -205,22 +216,14 @@ def sharded_kmeans(x_local: torch.Tensor, k: int, n_total: int, group=None, max_
             dist.all_reduce(out, group=group)
         return out
 
-    init_idx = torch.from_numpy(np.random.choice(n_total, k, replace=False).astype(np.int64))
-    centroids = fetch_rows(init_idx).contiguous()
-
-    i = 0
-    n_iters = 0
-    while max_iters is None or i < max_iters:
+    def accumulate(centroids):
         assign_accumulate(x_local, centroids, buf)
-        if distributed:
-            flat = torch.cat([buf["sums"].reshape(-1), buf["counts"].to(torch.float64)])
-            dist.all_reduce(flat, group=group)
-            buf["sums"].copy_(flat[: k * D].view(k, D))
-            buf["counts"].copy_(flat[k * D:].to(torch.int32))
-        counts_h = buf["counts"].cpu()
+        if distributed:                                    # in place, on the buffers the kernel wrote
+            dist.all_reduce(buf["sums"], group=group)
+            dist.all_reduce(buf["counts"], group=group)
+
+    def reseed_empty(centroids, counts_h):
         empty = torch.nonzero(counts_h == 0).flatten()
-        old = centroids.clone()
-        finalize(x_local, centroids, buf, None)            # means; empty clusters keep their old centroid for now
         if len(empty):
             if n_total <= 0:
                 raise ValueError("Can not choose random element from x, x is empty")
@@ -230,11 +233,48 @@ def sharded_kmeans(x_local: torch.Tensor, k: int, n_total: int, group=None, max_
                 dist.broadcast(d, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
                 draws = d.cpu()
             centroids[empty.to(dev)] = fetch_rows(draws)
-        shift = float((centroids - old).norm(dim=1).max().item())
-        n_iters = i + 1
-        if shift < stop_threshold:
-            break
-        i += 1
+
+    init_idx = torch.from_numpy(np.random.choice(n_total, k, replace=False).astype(np.int64))
+    centroids = fetch_rows(init_idx).contiguous()
+    check_every = max(1, int(check_every))
+    rec = torch.zeros((2, check_every), dtype=torch.float32, device=dev)     # [shift, any-empty] per iteration of the window
+    i = 0
+    n_iters = 0
+    done = False
+    while not done and (max_iters is None or i < max_iters):
+        snapshot, i0 = centroids.clone(), i
+        w = 0
+        while w < check_every and (max_iters is None or i < max_iters):      # ---- a window without host contact
+            accumulate(centroids)
+            old = centroids.clone()
+            finalize(x_local, centroids, buf, None)         # means; an empty cluster keeps its old centroid
+            rec[0, w] = (centroids - old).norm(dim=1).max()
+            rec[1, w] = (buf["counts"] == 0).any().float()
+            w += 1
+            i += 1
+        h = rec[:, :w].cpu()                                # the window's only synchronisation
+        if bool((h[1] > 0).any()):
+            # an empty cluster: replay this window the reference's way (host RNG draw in the iteration that needs it)
+            centroids.copy_(snapshot)
+            i = i0
+            for _ in range(w):
+                accumulate(centroids)
+                counts_h = buf["counts"].cpu()
+                old = centroids.clone()
+                finalize(x_local, centroids, buf, None)
+                reseed_empty(centroids, counts_h)
+                shift = float((centroids - old).norm(dim=1).max().item())
+                i += 1
+                n_iters = i
+                if shift < stop_threshold:
+                    done = True
+                    break
+        else:
+            n_iters = i
+            below = torch.nonzero(h[0] < stop_threshold).flatten()
+            if len(below):
+                n_iters = i0 + int(below[0]) + 1
+                done = True
     return centroids, buf["assign"], n_iters
 
 

@@ -16,10 +16,11 @@ TAU_ABS = 1e-6      # ~16 fp32 ulps of the operands xx + cc: below that the refe
 
 
 def assert_ids_match(ids, ref_ids, res, codebooks, what=""):
-    """ids/ref_ids [B,L].  Rows may differ from the fp32 reference only where the float64 oracle says the
-    top-2 gap is a near tie at the first differing level -- relative gap (d2 - d1) / d1 <= TAU, or, for rows that all but
-    coincide with a code (d1 is then a cancellation residue), (d2 - d1) <= TAU_ABS (xx + cc) -- and then only by
-    picking the runner-up.  Returns the number of such near-tie rows."""
+    """ids/ref_ids [B,L].  Rows may differ from the fp32 reference only where the float64 oracle says BOTH answers are
+    near-tied with the float64 minimum at the first differing level: distance excess (d - d_min) <= TAU * d_min, or, for rows
+    that all but coincide with a code (d_min is then a cancellation residue of terms ~1), (d - d_min) <= TAU_ABS (xx + cc).
+    (Several codes can be tied at once -- near-duplicate codes -- so membership in {best, runner-up} is not required.)
+    Returns the number of such near-tie rows."""
     from oracle import rq_oracle as O
     ids = np.asarray(ids).astype(np.int64).reshape(len(ids), -1)
     ref_ids = np.asarray(ref_ids).astype(np.int64).reshape(len(ref_ids), -1)
@@ -28,14 +29,20 @@ def assert_ids_match(ids, ref_ids, res, codebooks, what=""):
         return 0
     cbs64 = [np.asarray(c, np.float64) for c in codebooks]
     r64 = np.asarray(res, np.float64)[bad]
-    # both chains are identical up to the first differing level l, so one float64 pass following impl is enough
-    i64, second, gap, absgap = O.top2_gap(r64, cbs64, ids[bad], return_abs=True)
     for r in range(len(bad)):
-        l = int(np.nonzero(ids[bad[r]] != ref_ids[bad[r]])[0][0])
-        pair = {int(i64[r, l]), int(second[r, l])}
-        assert (gap[r, l] <= TAU or absgap[r, l] <= TAU_ABS) and int(ids[bad[r], l]) in pair and int(ref_ids[bad[r], l]) in pair, (
-            f"{what}: row {bad[r]} level {l}: impl {ids[bad[r]]} vs ref {ref_ids[bad[r]]}; "
-            f"fp64 says {i64[r]} / runner-up {second[r]} gap {gap[r, l]:.3e} (abs {absgap[r, l]:.3e})")
+        a, b = ids[bad[r]], ref_ids[bad[r]]
+        l = int(np.nonzero(a != b)[0][0])
+        resid = r64[r].copy()
+        for j in range(l):                       # both chains are identical up to the first differing level
+            resid -= cbs64[j][a[j]]
+        d = O.quantize_dist(resid[None, :], cbs64[l])[0]
+        dmin = d.min()
+        scale = (resid * resid).sum() + (cbs64[l][int(d.argmin())] ** 2).sum()
+        for k, who in ((int(a[l]), "impl"), (int(b[l]), "ref")):
+            exc = d[k] - dmin
+            assert exc <= TAU * max(abs(dmin), 1e-30) or exc <= TAU_ABS * max(scale, 1e-30), (
+                f"{what}: row {bad[r]} level {l}: impl {a} vs ref {b}; {who}'s code {k} is {exc:.3e} above the float64 "
+                f"minimum {dmin:.3e} (code {int(d.argmin())}; operand scale {scale:.3e})")
     return len(bad)
 
 

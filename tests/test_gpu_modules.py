@@ -218,7 +218,7 @@ def test_module_api_routes_to_the_tensor_core_tokeniser(D, hidden):
             res = res - layer.embedding.weight[ops.rq_tokenize(res, [layer.embedding.weight])[:, 0]]
     tok = SemanticIdTokenizer(input_dim=Din, output_dim=D, hidden_dims=list(hidden), codebook_size=K, n_layers=L, n_cat_feats=0).cuda()
     tok.rq_vae = m.eval()
-    tok.corpus_batch = 2048         # three batches (one ragged) -> one prepare, three tensor-core launches
+    tok.corpus_batch = 1700         # three batches (1700, 1700, 1600; all >= ops.TC_MIN_ROWS) -> one prepare, three tensor-core launches
 
     class Items:
         def __len__(self):
@@ -320,3 +320,68 @@ def test_mlp_bf16_path_is_opt_in_and_forward_only():
         assert torch.equal(ya, mlp(x))
     mlp.precision = "bf16"
     assert mlp(x).requires_grad                              # gradient needed -> falls to the exact, differentiable path
+
+
+@pytest.mark.parametrize("N,L,K,dup", [(5000, 3, 256, 0.3), (1, 3, 256, 0.0), (777, 2, 32, 0.9), (3000, 4, 256, 0.5)])
+def test_corpus_dedup_rank_and_id_statistics(N, L, K, dup):
+    """(f)-1: the dedup column (semids.py:94-108: rows j < i with the same tuple) and the diversity statistics of
+    train_rqvae.py:276-292 from the direct-table kernels, against the reference's own expressions (O(N^2) compare, torch.unique)."""
+    from rq_vae_recommender_b200 import ops
+    from rq_vae_recommender_b200.modules.tokenizer.semids import corpus_id_stats, dedup_rank
+    rs = np.random.RandomState(N + L)
+    ids = rs.randint(0, K, size=(N, L)).astype(np.int64)
+    ndup = int(dup * N)
+    if ndup:
+        ids[rs.choice(N, ndup, replace=False)] = ids[rs.choice(max(N // 10, 1), ndup)]     # many copies of a few tuples
+    ref_rank = (np.tril((ids[:, None, :] == ids[None, :, :]).all(-1), -1)).sum(1) if N <= 5000 else None
+    rank = dedup_rank(dev(ids), K)
+    assert np.array_equal(host(rank), ref_rank)
+    cached = torch.cat([dev(ids), rank.unsqueeze(1)], 1)
+    st = corpus_id_stats(cached, K)
+    t = torch.from_numpy(ids)
+    _, counts = torch.unique(t, dim=0, return_counts=True)                                # train_rqvae.py:279-283
+    p = counts / N
+    assert abs(float(st["rqvae_entropy"]) - float(-(p * torch.log(p)).sum())) < 1e-5
+    assert float(st["max_id_duplicates"]) == pytest.approx(ref_rank.max() / N)
+    for l in range(L):
+        assert float(st[f"codebook_usage_{l}"]) == pytest.approx(len(torch.unique(t[:, l])) / K)
+    if K ** L <= 2 ** 26:
+        r2, s2 = ops.sid_dedup_rank(dev(ids), K)
+        assert int(s2["n_unique"]) == len(counts) and int(s2["max_rank"]) == ref_rank.max()
+    else:
+        assert ops.sid_dedup_rank(dev(ids), K) is None           # 256^4 keys: the sort path answered above
+
+
+def test_sequence_gather_kernel_vs_reference_indexing():
+    """(f)-2: cached_ids[ids] with -1 under the padding mask and token_type_ids (semids.py:112-146) in one launch."""
+    from rq_vae_recommender_b200 import ops
+    rs = np.random.RandomState(3)
+    ncorp, C, B, S = 999, 4, 37, 20
+    cached = dev(rs.randint(0, 256, size=(ncorp, C)).astype(np.int64))
+    item = rs.randint(0, ncorp, size=(B, S)).astype(np.int64)
+    mask = rs.rand(B, S) > 0.3
+    item[~mask] = -1                                             # padded positions carry -1 like the reference's batches
+    out, tt = ops.sid_gather(cached, dev(item), dev(mask))
+    ref = cached[dev(item).flatten(), :].reshape(B, S * C)        # reference: index (wraps -1), then mask
+    m = dev(mask).repeat_interleave(C, dim=1)
+    ref[~m] = -1
+    assert torch.equal(out, ref)
+    assert torch.equal(tt, torch.arange(C, device="cuda").repeat(B, S))
+    fut, ttf = ops.sid_gather(cached, dev(item[:, :1].clip(0)), None)
+    assert torch.equal(fut, cached[dev(item[:, 0].clip(0))]) and torch.equal(ttf, torch.arange(C, device="cuda").repeat(B, 1))
+
+
+def test_forward_inside_a_compiled_caller():
+    """the modules must tolerate being called inside a torch.compile'd caller (the reference decorates
+    RqVae.forward, rqvae.py:141).  The ctypes entry points are marked torch.compiler.disable: Dynamo breaks the graph around
+    them instead of tracing into ctypes, and the compiled caller returns the eager result."""
+    g, x, _ = c1_inputs(0)
+    m, enc, dec, cbs = build("ste", 0)
+    m.train()
+    batch = batch_of(dev(x))
+    eager = m(batch, T)
+    compiled = torch.compile(lambda b, t: m(b, t), backend="eager")
+    out = compiled(batch, T)
+    assert torch.allclose(out.loss, eager.loss, rtol=1e-6) and torch.equal(out.embs_norm, eager.embs_norm)
+    out.loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())

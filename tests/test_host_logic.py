@@ -170,3 +170,30 @@ def test_sharded_kmeans_and_gathers_world2_match_single_process():
         assert np.array_equal(full, ref_ids)                       # all-gathered id table is in corpus order
         assert np.array_equal(usage, O.codebook_usage(ref_ids, 8))
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_sharded_kmeans_windowed_host_checks_equal_per_iteration_checks():
+    """The host is consulted once per window (check_every); a window that sees an empty cluster is rolled back and replayed with
+    the reference's per-iteration RNG draws (init/kmeans.py:48-54), so both schedules give the same centroids.  Duplicated
+    rows force duplicate initial centroids, i.e. empty clusters in the first iteration."""
+    from rq_vae_recommender_b200 import parallel
+    x = torch.from_numpy(I.randn(91, 64, 8))
+    x = torch.cat([x, x[:32]], 0)              # 96 rows, a third of them duplicates
+    outs = []
+    for every in (1, 4):
+        np.random.seed(11); torch.manual_seed(12)
+        cen, assign, iters = parallel.sharded_kmeans(x.clone(), 48, x.shape[0], max_iters=12, check_every=every,
+                                                     assign_accumulate=_cpu_assign_accumulate, finalize=_cpu_finalize,
+                                                     make_buf=_cpu_make_buf)
+        outs.append((cen.numpy(), assign.numpy().copy(), iters))
+    assert np.allclose(outs[0][0], outs[1][0], atol=1e-6)
+    assert np.array_equal(outs[0][1], outs[1][1])
+    # no empties, converging data: the windowed loop may only run PAST convergence, never stop early
+    y = torch.from_numpy(I.randn(92, 200, 8))
+    res = []
+    for every in (1, 4):
+        np.random.seed(13); torch.manual_seed(14)
+        cen, _, iters = parallel.sharded_kmeans(y.clone(), 8, 200, max_iters=40, check_every=every,
+                                                assign_accumulate=_cpu_assign_accumulate, finalize=_cpu_finalize, make_buf=_cpu_make_buf)
+        res.append((cen.numpy(), iters))
+    assert res[0][1] == res[1][1] and np.allclose(res[0][0], res[1][0], atol=1e-6)
