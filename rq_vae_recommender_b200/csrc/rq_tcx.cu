@@ -62,14 +62,15 @@
 #define TX_RIBUF 2                                // row-statistics buffers
 #else
 // 96 rows: image 144 KB.  Two thirds of the codebook bytes and of the per-level hand-offs per row, but shared memory is tight:
-// 3 codebook stages only when the id bytes of L <= 4 levels fit (else 2), 2 staging boxes of 12 KB, everything single-buffered.
-// Best for large batches (5 x 74 pair tiles cover 65 536 rows).
+// 2 codebook stages, 3 staging boxes of 12 KB, two TMEM buffers, single exchange buffer.  (A 3-stage codebook ring fits only
+// with 2 staging boxes and single-buffered row statistics; measured: 0.161 vs 0.155 ms at 65 536 rows -- the ring gains what
+// the stalled converter loses.)  Best for large batches (5 x 74 pair tiles cover 65 536 rows).
 #define TX_NBX 4                                  // 24 rows x 128 floats = 12 KB
-#define TX_NB_MAX 3
-#define TX_NX 2
+#define TX_NB_MAX 3                               // (tcx_run takes as many stages as fit: 2 at D = 768)
+#define TX_NX 3
 #define TX_NT 2
 #define TX_XBUF 1
-#define TX_RIBUF 1
+#define TX_RIBUF 2
 #endif
 #define TX_XBOX_ROWS (TX_R / TX_NBX)              // fp32 staging box rows.  512-byte box rows on purpose: with 128-byte rows the TMA
 #define TX_XBOX_COLS 128                          // engine delivered 13 B/clk/SM (profiles/r2_tcx_bringup.txt)

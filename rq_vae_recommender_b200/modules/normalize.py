@@ -6,6 +6,7 @@ from torch import Tensor
 from .. import ops
 
 
+@torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
 def l2norm(x, dim=-1, eps=1e-12):
     if dim not in (-1, x.dim() - 1):
         x = x.transpose(dim, -1)

@@ -44,6 +44,7 @@ class RqVaeComputedLosses(NamedTuple):
     p_unique_ids: Tensor
 
 
+@torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
 def count_unique_id_tuples(sem_ids: Tensor, codebook_size: int) -> Tensor:
     """#distinct rows of a [B,L] id table as a 0-d DEVICE tensor (no host sync in the training step).  Equals the reference's
     [B,B,L] triangular compare (rqvae.py:159-167: rows with no later duplicate) without the O(B^2) memory: the direct-table

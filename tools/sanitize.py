@@ -26,5 +26,11 @@ xm = dev(I.randn(6, 45, 70)).requires_grad_(True)
 ops.MLPFunction.apply(xm, True, *ws).sum().backward()
 np.random.seed(0); torch.manual_seed(0)
 Kmeans(k=16, max_iters=3).run(dev(I.randn(7, 500, 12)))
-ops.sid_histogram(torch.randint(0, 256, (1000, 3), device='cuda'), 256)
+ids3 = torch.randint(0, 256, (1000, 3), device='cuda')
+ops.sid_histogram(ids3, 256)
+rank, st = ops.sid_dedup_rank(ids3, 256)
+ops.sid_gather(torch.cat([ids3, rank.unsqueeze(1)], 1), torch.randint(0, 1000, (7, 20), device='cuda'), torch.rand(7, 20, device='cuda') > 0.3)
+# tc tokeniser at both tile shapes: several tiles per CTA pair, ragged tail
+x, cbs = I.rq_problem(30000, 768, 256, 3, seed=12)
+ops.rq_tokenize_tc(dev(x[:777]), [dev(c) for c in cbs]); ops.rq_tokenize_tc(dev(x), [dev(c) for c in cbs])
 torch.cuda.synchronize(); print("sanitize pass done")
