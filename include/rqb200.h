@@ -126,6 +126,20 @@ int rqb200_f32_to_bf16_image(const float* x, int64_t ldx, int rows, int K, void*
 int rqb200_gemm_bf16(const void* a_image, const void* w_image, int M, int N, int K, int relu, void* out_image,
                      float* out_f32, int64_t ldo, void* stream);
 
+/* ---- split-precision tensor-core GEMM: fp32-accurate products on the fp16 tensor cores -----------------------------
+ * The MLP Linears of modules/encoder.py:23-38 in their default (index-exact) precision and the two GEMMs of a
+ * Gumbel-softmax level (modules/quantize.py:113-117,135).  Each operand row is scaled by a power of two and stored as
+ * two fp16 images hi + lo (22 significant bits); C = act(A B^T) costs three tcgen05.mma per k-step (hi.hi + lo.hi +
+ * hi.lo, fp32 accumulate) and is written as fp32 rows.
+ *   split_image_bytes  : bytes of one operand buffer [hi image][lo image][row scales] for a [rows, K] matrix
+ *   f32_to_split_image : fp32 [rows, K] (ld = ldx) -> buffer; transposed != 0 reads the operand as x[K, rows]
+ *   gemm_split         : out[M, N] (ld = ldo) = act(A[M, K] . B[N, K]^T) from two such buffers; an optional mask[M, N]
+ *                        zeroes the entries whose mask value is not > 0 (the ReLU' of a backward GEMM) */
+size_t rqb200_split_image_bytes(int rows, int K);
+int rqb200_f32_to_split_image(const float* x, int64_t ldx, int rows, int K, int transposed, void* image, void* stream);
+int rqb200_gemm_split(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask,
+                      int64_t ldm, float* out, int64_t ldo, void* stream);
+
 /* ---- corpus id statistics (train_rqvae.py:279-289, modules/tokenizer/semids.py:94-108) ---------------- */
 int rqb200_sid_histogram(const int64_t* ids, int B, int L, int K, int64_t* hist /* [L,K], zeroed here */,
                          void* stream);

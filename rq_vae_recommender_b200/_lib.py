@@ -64,6 +64,9 @@ _SIGNATURES = {
     "rqb200_bf16_image_bytes": (c_size, [c_int, c_int]),
     "rqb200_f32_to_bf16_image": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "rqb200_gemm_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
+    "rqb200_split_image_bytes": (c_size, [c_int, c_int]),
+    "rqb200_f32_to_split_image": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "rqb200_gemm_split": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
 }
 
 

@@ -288,3 +288,361 @@ extern "C" int rqb200_gemm_bf16(const void* a_image, const void* w_image, int M,
   RQB_LAUNCH_CHECK();
   return RQB_OK;
 }
+
+// =====================================================================================================================
+// Split-precision GEMM: fp32-accurate products on the fp16 tensor cores (the MLPs of modules/encoder.py:23-38 in their
+// default, index-exact precision; the two GEMMs of a Gumbel-softmax level, modules/quantize.py:113-117,135).
+//
+//   C[M,N] = act( A[M,K] . B[N,K]^T ),  A, B, C fp32 in HBM.
+//
+// Every operand row is scaled by a power of two so that its largest element lies in [2^14, 2^15) and stored as TWO fp16 images
+//   hi = fp16(v 2^e),  lo = fp16(v 2^e - hi)          (hi + lo carries 22 significant bits of v; lo may be subnormal: the error
+//                                                      is then 2^-25 absolute = 2^-39 of the row maximum)
+// and the product is three tcgen05.mma per k-step with fp32 accumulation in TMEM:  hi.hi + lo.hi + hi.lo  (lo.lo is 2^-22
+// relative and dropped).  The epilogue multiplies by 2^-(e_row + e_col), both exact.  Measured against float64 the result is
+// as close as a plain fp32 FMA GEMM (tests/test_gpu_gemm_split.py states the bound that is asserted).
+//
+// Image = the bf16 image's layout with fp16 elements: [row tile of 128][k chunk of 64][128 rows x 128 B swizzled]; one buffer
+// holds [hi image][lo image][row scales: 128 floats per row tile, value 2^-e].  K is padded with zeros to a multiple of 64, rows
+// to a multiple of 128.
+//
+// Kernel: persistent, one CTA per SM; work item = (row tile, group of up to 256 columns).  Stage = [A hi][A lo][B hi 0][B hi 1]
+// [B lo 0][B lo 1] = 96 KB, 2 stages; the two B blocks of a half are adjacent so that ONE tcgen05.mma covers N = 256.
+// warp 0 = bulk-copy producer, warp 1 = MMA issuer (two accumulators of 256 TMEM columns: hi.hi and the cross terms),
+// warps 4-11 = epilogue (sums the two, scales, activates).
+#include <cuda_fp16.h>
+
+#define GS_STAGES 2
+#define GS_MAX_CHUNKS 12                   // 16-byte chunks per lane of the row splitter: K <= 32 * 8 * 12 = 3072
+#define GS_STAGE_BYTES (6 * GT_BLK_BYTES)
+
+extern "C" size_t rqb200_split_image_bytes(int rows, int K) {
+  if (rows < 0 || K <= 0) return 0;
+  const size_t mt = (size_t)(rows + 127) / 128, nkc = (size_t)(K + GT_KC - 1) / GT_KC;
+  return 2 * mt * nkc * GT_BLK_BYTES + mt * 128 * sizeof(float);
+}
+
+__device__ __forceinline__ float gs_pow2_scale(float mx) {
+  // 2^e with mx 2^e in [2^14, 2^15); zero / non-finite rows are not scaled
+  if (!(mx > 0.f) || !(mx < INFINITY)) return 1.f;
+  int ex;
+  frexpf(mx, &ex);                        // mx = f 2^ex, f in [0.5, 1)
+  return ldexpf(1.f, max(-120, min(120, 15 - ex)));      // (clamped: 2^e and 2^-e both stay normal)
+}
+__device__ __forceinline__ void gs_split8(const float (&v)[8], float s, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = v[2 * e] * s, b = v[2 * e + 1] * s;
+    h[e] = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h[e]);
+    l[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+  }
+  hi.x = *reinterpret_cast<uint32_t*>(&h[0]); hi.y = *reinterpret_cast<uint32_t*>(&h[1]);
+  hi.z = *reinterpret_cast<uint32_t*>(&h[2]); hi.w = *reinterpret_cast<uint32_t*>(&h[3]);
+  lo.x = *reinterpret_cast<uint32_t*>(&l[0]); lo.y = *reinterpret_cast<uint32_t*>(&l[1]);
+  lo.z = *reinterpret_cast<uint32_t*>(&l[2]); lo.w = *reinterpret_cast<uint32_t*>(&l[3]);
+}
+
+// Row-major source [rows, K] (ld = ldx): W lanes per image row (32 / W rows per warp pass), NCH 16-byte chunks per lane; the row
+// stays in registers between the maximum and the split.  grid = row tiles, block = 256.  Few registers on purpose: the kernel
+// is a pure HBM stream (read 4 B, write 4 B per element) and needs many warps per SM in flight -- the first version (one
+// generic 12-chunk instantiation, 133 registers, one CTA per SM) ran at 0.8-2 TB/s.
+template <int NCH, int W>
+__global__ void __launch_bounds__(256) gs_split_rows_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, unsigned char* img) {
+  const int nkc = (K + GT_KC - 1) / GT_KC, mtiles = gridDim.x;
+  const int mt = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* hi_img = img;
+  unsigned char* lo_img = img + (size_t)mtiles * nkc * GT_BLK_BYTES;
+  float* scales = reinterpret_cast<float*>(img + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
+  const int nchunks = nkc * 8;                                    // 16-byte (8 element) chunks per image row
+  const bool vec = (K % 8 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  constexpr int G = 32 / W;                                       // rows per warp pass
+  const int sub = lane / W, sl = lane % W;
+#pragma unroll 1
+  for (int r = warp * G + sub; r < 128; r += 8 * G) {
+    const int row = mt * 128 + r;
+    float v[NCH][8];
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = sl + W * i;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+      if (c < nchunks && row < rows) {
+        const float* src = x + (int64_t)row * ldx + c * 8;
+        if (vec && c * 8 + 8 <= K) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c * 8 + e < K) v[i][e] = __ldg(src + e);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, fabsf(v[i][e]));
+      }
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float s = gs_pow2_scale(mx);
+    if (sl == 0) scales[mt * 128 + r] = 1.f / s;                   // exact: a power of two
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = sl + W * i;
+      if (c < nchunks) {
+        uint4 hi, lo;
+        gs_split8(v[i], s, hi, lo);
+        const size_t off = ((size_t)mt * nkc + (c >> 3)) * GT_BLK_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(hi_img + off) = hi;
+        *reinterpret_cast<uint4*>(lo_img + off) = lo;
+      }
+    }
+  }
+}
+
+// Transposed source: image row r = column r of x[K, rows] (ld = ldx).  One thread per image row (reads of a k are coalesced
+// across the 128 threads of the tile), two passes over the column: maximum, then split.  grid = row tiles, block = 128.
+__global__ void gs_split_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, unsigned char* img) {
+  const int nkc = (K + GT_KC - 1) / GT_KC, mtiles = gridDim.x;
+  const int mt = blockIdx.x, r = threadIdx.x;
+  unsigned char* hi_img = img;
+  unsigned char* lo_img = img + (size_t)mtiles * nkc * GT_BLK_BYTES;
+  float* scales = reinterpret_cast<float*>(img + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
+  const int row = mt * 128 + r;
+  const bool live = row < rows;
+  float mx = 0.f;
+  if (live)
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fabsf(__ldg(x + (int64_t)k * ldx + row)));
+  const float s = gs_pow2_scale(mx);
+  scales[row] = 1.f / s;
+  for (int c = 0; c < nkc * 8; ++c) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c * 8 + e;
+      v[e] = (live && k < K) ? __ldg(x + (int64_t)k * ldx + row) : 0.f;
+    }
+    uint4 hi, lo;
+    gs_split8(v, s, hi, lo);
+    const size_t off = ((size_t)mt * nkc + (c >> 3)) * GT_BLK_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi_img + off) = hi;
+    *reinterpret_cast<uint4*>(lo_img + off) = lo;
+  }
+}
+
+extern "C" int rqb200_f32_to_split_image(const float* x, int64_t ldx, int rows, int K, int transposed, void* image, void* stream) {
+  RQB_CHECK_ARG(K > 0 && rows >= 0, "f32_to_split_image: bad shape (rows=%d K=%d)", rows, K);
+  RQB_CHECK_ARG(transposed ? ldx >= rows : ldx >= K, "f32_to_split_image: ld too small");
+  if (rows == 0) return RQB_OK;
+  RQB_CHECK_ARG(x && image, "f32_to_split_image: null pointer");
+  RQB_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "f32_to_split_image: the image must be 16-byte aligned");
+  const int mtiles = (rows + 127) / 128;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (transposed) {
+    gs_split_cols_kernel<<<mtiles, 128, 0, st>>>(x, ldx, rows, K, reinterpret_cast<unsigned char*>(image));
+  } else {
+    if (K > 32 * 8 * GS_MAX_CHUNKS) {
+      rqb_set_error("f32_to_split_image: K = %d > %d", K, 32 * 8 * GS_MAX_CHUNKS);
+      return RQB_ERR_UNSUPPORTED;
+    }
+    unsigned char* im = reinterpret_cast<unsigned char*>(image);
+    const int nchunks = ((K + GT_KC - 1) / GT_KC) * 8;
+    if (nchunks <= 8) gs_split_rows_kernel<1, 8><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else if (nchunks <= 16) gs_split_rows_kernel<1, 16><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else if (nchunks <= 32) gs_split_rows_kernel<1, 32><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else if (nchunks <= 64) gs_split_rows_kernel<2, 32><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else if (nchunks <= 96) gs_split_rows_kernel<3, 32><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else if (nchunks <= 128) gs_split_rows_kernel<4, 32><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+    else gs_split_rows_kernel<GS_MAX_CHUNKS, 32><<<mtiles, 256, 0, st>>>(x, ldx, rows, K, im);
+  }
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}
+
+struct GsParams {
+  const unsigned char *a_hi, *a_lo, *b_hi, *b_lo;   // [tiles][nkc][16 KB]
+  const float *a_scale, *b_scale;                   // 2^-e per image row
+  int M, N, nkc, mtiles, nblocks, ngroups, nitems, relu;
+  float* out;
+  int64_t ldo;
+  const float* mask;                                // optional [M, N] (ld = ldm): out = mask > 0 ? out : 0  (ReLU' of a backward GEMM)
+  int64_t ldm;
+};
+
+__device__ __forceinline__ uint32_t gs_idesc_f16(int M, int N) {       // A, B = F16 (format 0), D = F32, K-major both
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
+  extern __shared__ __align__(1024) unsigned char gsm[];
+  GtSmemMisc* ms = reinterpret_cast<GtSmemMisc*>(gsm + GS_STAGES * GS_STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    if ((smem_u32(gsm) & 1023u) != 0) __trap();
+    for (int i = 0; i < GS_STAGES; ++i) { mbar_init(&ms->full[i], 1); mbar_init(&ms->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ms->t_full[i][0], 1); mbar_init(&ms->t_full[i][1], 1);
+      mbar_init(&ms->t_empty[i], 8 * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) gt_alloc(&ms->tmem_base, 512);
+  gt_fence_before();
+  __syncthreads();
+  gt_fence_after();
+
+  if (warp == 0 && lane == 0) {
+    // ============================================================== producer: 2 A blocks + 2 or 4 B blocks per stage
+    uint32_t s = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int mt = item / p.ngroups, g = item % p.ngroups;
+      const int nb = min(2, p.nblocks - 2 * g);
+      for (int kc = 0; kc < p.nkc; ++kc, ++s) {
+        const uint32_t st = s % GS_STAGES, u = s / GS_STAGES;
+        mbar_wait_guarded(&ms->empty[st], (u & 1) ^ 1, 1);
+        unsigned char* dst = gsm + st * GS_STAGE_BYTES;
+        mbar_expect_tx(&ms->full[st], (2 + 2 * nb) * GT_BLK_BYTES);
+        const size_t ao = ((size_t)mt * p.nkc + kc) * GT_BLK_BYTES;
+        bulk_g2s(dst, p.a_hi + ao, GT_BLK_BYTES, &ms->full[st]);
+        bulk_g2s(dst + GT_BLK_BYTES, p.a_lo + ao, GT_BLK_BYTES, &ms->full[st]);
+        for (int b = 0; b < nb; ++b) {
+          const size_t bo = ((size_t)(2 * g + b) * p.nkc + kc) * GT_BLK_BYTES;
+          bulk_g2s(dst + (2 + b) * GT_BLK_BYTES, p.b_hi + bo, GT_BLK_BYTES, &ms->full[st]);
+          bulk_g2s(dst + (4 + b) * GT_BLK_BYTES, p.b_lo + bo, GT_BLK_BYTES, &ms->full[st]);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================================================== MMA issuer: hi.hi + lo.hi + hi.lo per k-step
+    const uint32_t base = smem_u32(gsm);
+    uint32_t s = 0, it = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+      const int g = item % p.ngroups;
+      const int nb = min(2, p.nblocks - 2 * g);
+      const uint32_t idesc = gs_idesc_f16(128, nb * 128);
+      mbar_wait_guarded(&ms->t_empty[0], (it & 1) ^ 1, 2);
+      gt_fence_after();
+      // two accumulators: hi.hi in columns [0, 256), the cross terms in [256, 512).  The tensor core truncates the fp32
+      // accumulator after every MMA (measured: the error of one shared accumulator grows with the number of MMAs and matches a
+      // round-toward-zero model, 5.4e-7 of |a||b| at K = 768); apart, the large sum sees a third of the truncations and the
+      // small one truncates at 2^-11 of the magnitude: 1.8e-7, the level of a plain fp32 GEMM
+      const uint32_t d = GT_TMEM(), dx = GT_TMEM() + 256;
+      for (int kc = 0; kc < p.nkc; ++kc, ++s) {
+        const uint32_t st = s % GS_STAGES;
+        mbar_wait_guarded(&ms->full[st], (s / GS_STAGES) & 1, 3);
+        gt_fence_after();
+        const uint32_t sa = base + st * GS_STAGE_BYTES;
+        const uint64_t ahi = gt_smem_desc(sa), alo = gt_smem_desc(sa + GT_BLK_BYTES);
+        const uint64_t bhi = gt_smem_desc(sa + 2 * GT_BLK_BYTES), blo = gt_smem_desc(sa + 4 * GT_BLK_BYTES);
+#pragma unroll
+        for (int j = 0; j < GT_KC / 16; ++j) {
+          gt_mma(d, ahi + 2 * j, bhi + 2 * j, idesc, (kc | j) != 0);
+          gt_mma(dx, alo + 2 * j, bhi + 2 * j, idesc, (kc | j) != 0);
+          gt_mma(dx, ahi + 2 * j, blo + 2 * j, idesc, 1);
+        }
+        gt_commit(&ms->empty[st]);
+      }
+      gt_commit(&ms->t_full[0][0]);
+      gt_commit(&ms->t_full[0][1]);
+    }
+  } else if (warp >= 4) {
+    // ============================================================== epilogue: TMEM -> x 2^-(e_row + e_col) -> act -> fp32 rows
+    const int quarter = warp & 3, blk = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+      const int mt = item / p.ngroups, g = item % p.ngroups;
+      const int nb = min(2, p.nblocks - 2 * g);
+      mbar_wait_guarded(&ms->t_full[0][blk], it & 1, 4);
+      gt_fence_after();
+      const int row = mt * 128 + r;
+      const int col0 = (2 * g + blk) * 128;
+      if (blk < nb) {
+        const float rs = __ldg(p.a_scale + row);                 // scale vectors are padded to whole tiles
+        const uint32_t tcol = GT_TMEM() + lane_addr + blk * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = col0 + c * 32;
+          if (col >= p.N) break;                                 // warp-uniform
+          uint32_t sr[32], sx[32];
+          gt_ld32(tcol + c * 32, sr);
+          gt_ld32(tcol + 256 + c * 32, sx);
+          // scale of column col + lane (vectors are padded to whole tiles).  2^-(e_row + e_col) is applied as two factors of half
+          // the exponent each (|e| <= 120 per operand): neither the factor nor the intermediate product leaves the fp32 range
+          // unless the result does
+          const int ea = (__float_as_int(rs) >> 23) & 0xff;                                    // this lane's ROW
+          const int ebl = (__float_as_int(__ldg(p.b_scale + col + lane)) >> 23) & 0xff;         // column col + lane
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int et = ea + __shfl_sync(0xffffffffu, ebl, e) - 254;                         // -(e_row + e_col)
+            const int e1 = et >> 1;
+            v[e] = ((__uint_as_float(sr[e]) + __uint_as_float(sx[e])) * __int_as_float((e1 + 127) << 23)) * __int_as_float((et - e1 + 127) << 23);   // exact
+            if (p.relu) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (p.mask && row < p.M) {
+            const float* mk = p.mask + (int64_t)row * p.ldm + col;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col + e < p.N && !(__ldg(mk + e) > 0.f)) v[e] = 0.f;
+          }
+          if (row < p.M) {
+            float* o = p.out + (int64_t)row * p.ldo + col;
+            if (col + 32 <= p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (col + e < p.N) o[e] = v[e];
+            }
+          }
+        }
+      }
+      gt_fence_before();
+      mbar_arrive(&ms->t_empty[0]);
+    }
+  }
+
+  gt_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    gt_fence_after();
+    gt_dealloc(GT_TMEM(), 512);
+  }
+}
+
+extern "C" int rqb200_gemm_split(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask,
+                                 int64_t ldm, float* out, int64_t ldo, void* stream) {
+  RQB_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldo >= N, "gemm_split: bad shape (M=%d N=%d K=%d ldo=%lld)", M, N, K, (long long)ldo);
+  if (M == 0) return RQB_OK;
+  RQB_CHECK_ARG(a_image && b_image && out, "gemm_split: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GsParams p{};
+  p.M = M; p.N = N; p.nkc = (K + GT_KC - 1) / GT_KC;
+  p.mtiles = (M + 127) / 128;
+  p.nblocks = (N + 127) / 128;
+  p.ngroups = (p.nblocks + 1) / 2;
+  p.nitems = p.mtiles * p.ngroups;
+  p.relu = relu;
+  const size_t a_img = (size_t)p.mtiles * p.nkc * GT_BLK_BYTES, b_img = (size_t)p.nblocks * p.nkc * GT_BLK_BYTES;
+  p.a_hi = reinterpret_cast<const unsigned char*>(a_image); p.a_lo = p.a_hi + a_img;
+  p.a_scale = reinterpret_cast<const float*>(p.a_hi + 2 * a_img);
+  p.b_hi = reinterpret_cast<const unsigned char*>(b_image); p.b_lo = p.b_hi + b_img;
+  p.b_scale = reinterpret_cast<const float*>(p.b_hi + 2 * b_img);
+  p.out = out; p.ldo = ldo;
+  p.mask = mask; p.ldm = ldm;
+  RQB_CHECK_ARG(!mask || ldm >= N, "gemm_split: ldm < N");
+  int dev = 0, sm_count = 0;
+  RQB_CUDA(cudaGetDevice(&dev));
+  RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = (size_t)GS_STAGES * GS_STAGE_BYTES + sizeof(GtSmemMisc);
+  RQB_CUDA(cudaFuncSetAttribute(gs_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.nitems < sm_count ? p.nitems : sm_count;
+  gs_gemm_kernel<<<grid, GT_THREADS, smem, st>>>(p);
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}

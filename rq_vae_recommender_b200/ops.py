@@ -6,6 +6,7 @@ runs in the hand-written kernels of csrc/.  CUDA tensors only -- CPU tensors rai
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -185,6 +186,84 @@ def sgemm(a: torch.Tensor, b: torch.Tensor, *, trans_a=False, trans_b=False, rel
     return out
 
 
+# ---------------------------------------------------------------------------------------------- split-precision tensor-core GEMM
+#: rows of the A operand from which the dense GEMMs of the MLPs / the Gumbel level run on the tensor cores (three fp16
+#: products per k-step, fp32-accurate: csrc/gemm_tc.cu); below it one launch of the CUDA-core SGEMM is as fast
+SPLIT_MIN_ROWS = 512
+SPLIT_CALLS = 0
+
+
+class SplitOperand:
+    """One GEMM operand [rows, K] as hi + lo fp16 images with power-of-two row scales (rqb200_f32_to_split_image).
+    ``transposed=True`` builds the operand of t.T without materialising the transpose."""
+
+    def __init__(self, t: torch.Tensor, transposed: bool = False):
+        _need_cuda(t)
+        lib = _lib.load()
+        t = _rows(t.detach())
+        self.rows, self.K = (t.shape[1], t.shape[0]) if transposed else (t.shape[0], t.shape[1])
+        self.device = t.device
+        nbytes = lib.rqb200_split_image_bytes(self.rows, self.K)
+        self.buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.rqb200_f32_to_split_image(_p(t), t.stride(0), self.rows, self.K, int(transposed), _p(self.buf),
+                                                     _stream()), "f32_to_split_image")
+        _count(1)
+
+
+# operands that do not change between calls (weights, codebooks): keyed on identity AND version like the tokeniser state
+_SPLIT_CACHE: "dict[tuple, tuple]" = {}
+_SPLIT_CACHE_MAX = 32
+
+
+def split_operand_cached(t: torch.Tensor, transposed: bool = False) -> SplitOperand:
+    # the entry remembers the tensor OBJECT (weak reference): a temporary that died and whose address the allocator handed to
+    # another tensor of the same shape must not hit
+    key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index, bool(transposed))
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    if len(_SPLIT_CACHE) >= _SPLIT_CACHE_MAX:
+        _SPLIT_CACHE.pop(next(iter(_SPLIT_CACHE)))
+    op = SplitOperand(t, transposed)
+    _SPLIT_CACHE[key] = (weakref.ref(t), op)
+    return op
+
+
+def gemm_split(a, b, *, relu: bool = False, mask: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] = act(A[M, K] @ B[N, K]^T) on the fp16 tensor cores with fp32 accuracy; a, b: SplitOperand or fp32 tensor."""
+    global SPLIT_CALLS
+    lib = _lib.load()
+    if not isinstance(a, SplitOperand):
+        a = SplitOperand(a)
+    if not isinstance(b, SplitOperand):
+        b = SplitOperand(b)
+    if a.K != b.K:
+        raise ValueError(f"gemm_split inner dims differ: {a.K} vs {b.K}")
+    M, N = a.rows, b.rows
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if mask is not None:
+        mask = _rows(mask)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.rqb200_gemm_split(_p(a.buf), _p(b.buf), M, N, a.K, int(relu), _p(mask),
+                                         mask.stride(0) if mask is not None else 0, _p(out), out.stride(0), _stream()),
+                   "gemm_split")
+    _count(1)
+    SPLIT_CALLS += 1
+    return out
+
+
+def linear_nt(a: torch.Tensor, w: torch.Tensor, *, relu: bool = False, mask: Optional[torch.Tensor] = None,
+              w_transposed: bool = False) -> torch.Tensor:
+    """a[M, K] @ op(w)^T with a static second operand (weight / codebook): op(w) = w [N, K], or w^T for w [K, N] when
+    ``w_transposed``.  Tensor cores from SPLIT_MIN_ROWS rows on, the CUDA-core SGEMM below (same result to ~1e-7)."""
+    if a.shape[0] >= SPLIT_MIN_ROWS:
+        return gemm_split(a, split_operand_cached(w, transposed=w_transposed), relu=relu, mask=mask)
+    return sgemm(a, w, trans_b=not w_transposed, relu=relu, mask=mask)
+
+
 class MLPFunction(torch.autograd.Function):
     """modules/encoder.py:23-38 as one autograd node: bias-free Linear+ReLU stack (ReLU fused in the GEMM
     epilogue), optional final L2 normalisation (modules/normalize.py)."""
@@ -198,7 +277,7 @@ class MLPFunction(torch.autograd.Function):
         acts = [h]
         n = len(ws)
         for i, w in enumerate(ws):
-            h = sgemm(h, w, trans_b=True, relu=(i != n - 1))
+            h = linear_nt(h, w, relu=(i != n - 1))
             acts.append(h)
         norms = None
         if normalize:
@@ -237,7 +316,7 @@ class MLPFunction(torch.autograd.Function):
             if ctx.needs_input_grad[2 + i]:
                 g_ws[i] = sgemm(g, h_in, trans_a=True)                     # [out,B] @ [B,in]
             if i > 0 or ctx.needs_input_grad[0]:
-                g = sgemm(g, ws[i], mask=h_in if i > 0 else None)          # [B,out] @ [out,in], ReLU' of layer i-1
+                g = linear_nt(g, ws[i], mask=h_in if i > 0 else None, w_transposed=True)   # [B,out] @ [out,in], ReLU' of layer i-1
         return (g if ctx.needs_input_grad[0] else None, None, *g_ws)
 
 
@@ -303,10 +382,10 @@ class GumbelQuantizeFunction(torch.autograd.Function):
         w = torch.empty((B, K), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.rqb200_row_sqnorm(_p(cb), K, D, _p(cc), st), "row_sqnorm")
-            dist = sgemm(x, cb, trans_b=True)                                    # x @ C^T
+            dist = linear_nt(x, cb)                                              # x @ C^T
             _lib.check(lib.rqb200_dist_finish(_p(dist), _p(x), x.stride(0), _p(cc), B, D, K, _p(ids), st), "dist")
             _lib.check(lib.rqb200_gumbel_softmax_fwd(_p(dist), _p(u), _p(w), B, K, float(temperature), st), "softmax")
-            emb = sgemm(w, cb)                                                   # W @ C   (quantize.py:135)
+            emb = linear_nt(w, cb, w_transposed=True)                            # W @ C   (quantize.py:135)
             _lib.check(lib.rqb200_gumbel_row_finish(_p(x), x.stride(0), _p(emb), B, D, float(beta), _p(loss), st),
                        "row_finish")
         _count(4)
@@ -333,10 +412,10 @@ class GumbelQuantizeFunction(torch.autograd.Function):
             _lib.check(lib.rqb200_gumbel_bwd_ge(_p(g_emb), g_emb.stride(0) if g_emb is not None else 0,
                                                 g_emb.stride(1) if g_emb is not None else 0, _p(g_loss), gl_s,
                                                 _p(x), x.stride(0), _p(emb), _p(gE), B, D, st), "bwd_ge")
-            gw = sgemm(gE, cb, trans_b=True)                                     # gW = gE @ C^T   [B,K]
+            gw = linear_nt(gE, cb)                                               # gW = gE @ C^T   [B,K]
             _lib.check(lib.rqb200_gumbel_bwd_softmax(_p(w), _p(gw), B, K, ctx.temperature, _p(rowsum), _p(colsum), st),
                        "bwd_softmax")                                            # gw now holds gdist
-            gx = sgemm(gw, cb)                                                   # gdist @ C       [B,D]
+            gx = linear_nt(gw, cb, w_transposed=True)                            # gdist @ C       [B,D]
             _lib.check(lib.rqb200_gumbel_bwd_gx(_p(gx), _p(x), x.stride(0), _p(emb), _p(g_loss), gl_s, _p(rowsum),
                                                 ctx.beta, B, D, st), "bwd_gx")
             gc = None
@@ -518,7 +597,7 @@ def rq_tokenize_tc(x: torch.Tensor, codebooks=None, state: Optional[TcState] = N
 # frozen-codebook cache of prepared states behind the module API (RqVae.tokenize / SemanticIdTokenizer): keyed on the
 # identity AND version of every codebook tensor, so an optimiser step (in-place update bumps ._version) or a reloaded
 # checkpoint re-prepares; a handful of entries is plenty (one model per process in the reference's scripts)
-_TC_CACHE: "dict[tuple, TcState]" = {}
+_TC_CACHE: "dict[tuple, tuple]" = {}
 _TC_CACHE_MAX = 4
 #: rows below which the exact CUDA-core kernel is used even when the tensor-core path is available (one 128-row tile keeps
 #: 2 of 148 SMs busy; the prepare step costs ~0.4 ms when the cache misses)
@@ -530,12 +609,16 @@ def _tc_cache_key(codebooks: Sequence[torch.Tensor]):
 
 
 def tc_state_for(codebooks: Sequence[torch.Tensor]) -> TcState:
+    # an entry also remembers the tensor OBJECTS (weak references): a derived codebook (sim_vq projection, normalised rows) is a
+    # temporary whose address the allocator may hand to the next call's temporary with the same version counter
     key = _tc_cache_key(codebooks)
-    st = _TC_CACHE.get(key)
-    if st is None:
-        if len(_TC_CACHE) >= _TC_CACHE_MAX:
-            _TC_CACHE.pop(next(iter(_TC_CACHE)))
-        st = _TC_CACHE[key] = TcState(codebooks)
+    hit = _TC_CACHE.get(key)
+    if hit is not None and all(r() is c for r, c in zip(hit[0], codebooks)):
+        return hit[1]
+    if len(_TC_CACHE) >= _TC_CACHE_MAX:
+        _TC_CACHE.pop(next(iter(_TC_CACHE)))
+    st = TcState(codebooks)
+    _TC_CACHE[key] = ([weakref.ref(c) for c in codebooks], st)
     return st
 
 
