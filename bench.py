@@ -16,6 +16,10 @@ own shard (items are independent: weak scaling, no data-path collective); the ti
                 int32 id blocks + all-reduce of the [L,K] usage counts per step, checked against one GPU tokenising the whole
                 corpus; plus one Lloyd iteration (assign + fp64 accumulate + all-reduce + update) at 20 000 x 32 and x 768
 
+  c2            (N = 1) BASELINE config 2: 12 101 x 768 items, device-timed through the module-API routing (ops.rq_tokenize_auto)
+  pipeline      (N = 1) the shipped architecture: 768-512-256-128-32 encoder (split-precision tensor-core GEMMs) + 3-level RQ at
+                D = 32, 65 536 items, index-exact precision: encoder ms, tokenise ms, id agreement with the CUDA-core SGEMM path
+
 --impl reference times that CPU port as the reference arm (the reference is pure Python/PyTorch: there is nothing
 to compile into oracle/_ref).
 """
@@ -264,6 +268,75 @@ def run_c3(world, rank, cbs, torch, dist, ops, parallel):
     return out
 
 
+def _event_ms(torch, fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def run_c2(x, cbs, torch, ops):
+    """BASELINE configs[1]: ~12K x 768 items on one B200, through the routing the module API uses."""
+    n = 12101
+    xs = x[:n].contiguous()
+    with torch.no_grad():
+        ms = _event_ms(torch, lambda: ops.rq_tokenize_auto(xs, cbs), n=20)
+        same = bool(torch.equal(ops.rq_tokenize_auto(xs, cbs), ops.rq_tokenize(xs, cbs)))
+    return {"items": n, "ms": ms, "items_per_sec": n / (ms * 1e-3), "ids_equal_exact_kernel": same,
+            "timed": "ops.rq_tokenize_auto (cached prepared state), device resident"}
+
+
+def run_pipeline(torch, ops):
+    """Shipped architecture end to end on the device: encoder MLP 768-512-256-128-32 + 3-level RQ (K = 256, D = 32), 65 536 items,
+    default (index-exact) precision.  Codebooks are k-means-initialised on the encoder outputs of clustered synthetic items, so
+    the codes are live and id agreement is meaningful."""
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    torch.manual_seed(0)
+    np.random.seed(0)
+    m = RqVae(input_dim=768, embed_dim=32, hidden_dims=[512, 256, 128], codebook_size=256, codebook_kmeans_init=True,
+              codebook_mode=QuantizeForwardMode.STE, n_layers=3, n_cat_features=0).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    centers = torch.nn.functional.normalize(torch.randn(200, 768, device="cuda", generator=g), dim=1)
+
+    def items(n):
+        v = centers[torch.randint(0, 200, (n,), device="cuda", generator=g)]
+        v = v + 0.5 * torch.nn.functional.normalize(torch.randn(n, 768, device="cuda", generator=g), dim=1)
+        return torch.nn.functional.normalize(v, dim=1)
+
+    m.train()
+    with torch.no_grad():
+        m(SeqBatch(None, None, None, items(20000), None, None), 0.2)     # lazy k-means init (train_rqvae.py:178-183)
+    m.eval()
+    x = items(N_ITEMS)
+    with torch.no_grad():
+        enc_ms = _event_ms(torch, lambda: m.encode(x))
+        tok_ms = _event_ms(torch, lambda: m.tokenize(x))
+        ids = m.tokenize(x)
+        calls0 = ops.SPLIT_CALLS
+        m.encode(x)
+        on_tc = ops.SPLIT_CALLS - calls0
+        old, ops.SPLIT_MIN_ROWS = ops.SPLIT_MIN_ROWS, 1 << 62            # the CUDA-core SGEMM path for comparison
+        try:
+            sg_ms = _event_ms(torch, lambda: m.encode(x), n=2, warm=1)
+            ids_sg = m.tokenize(x)
+        finally:
+            ops.SPLIT_MIN_ROWS = old
+    flop = 2.0 * N_ITEMS * (768 * 512 + 512 * 256 + 256 * 128 + 128 * 32)
+    return {"items": N_ITEMS, "encoder_ms": enc_ms, "tokenize_ms": tok_ms, "items_per_sec": N_ITEMS / (tok_ms * 1e-3),
+            "encoder_tflops_fp32_equivalent": flop / (enc_ms * 1e-3) / 1e12, "encoder_gemms_on_tensor_cores": on_tc,
+            "encoder_ms_cuda_core_sgemm": sg_ms,
+            "ids_rows_equal_sgemm_path": float((ids == ids_sg).all(1).float().mean().item()),
+            "unique_id_tuples": int(torch.unique(ids, dim=0).shape[0])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,6 +503,12 @@ def main():
         }
         if c3 is not None:
             out["c3"] = c3
+        if world == 1:
+            for name, fn in (("c2", lambda: run_c2(x, cbs, torch, ops)), ("pipeline", lambda: run_pipeline(torch, ops))):
+                try:
+                    out[name] = fn()
+                except Exception as e:        # an auxiliary record must never take the headline line down
+                    out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             v, threads, sample = cpu_port_items_per_sec(x_h, cbs_h)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}

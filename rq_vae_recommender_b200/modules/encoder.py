@@ -56,9 +56,18 @@ class MLP(nn.Module):
             object.__setattr__(self, "_wimg_cache", cache)
         return cache[1]
 
-    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
     def forward(self, x: Tensor) -> Tensor:
         assert x.shape[-1] == self.input_dim, f"Invalid input dim: Expected {self.input_dim}, found {x.shape[-1]}"
+        if torch.compiler.is_compiling() and self.precision == "fp32" and not (self.dropout != 0 and self.training):
+            # inside torch.compile (the reference compiles RqVae.forward, rqvae.py:141): one custom-operator node, no graph break
+            from .. import library
+            weights = [m.weight for m in self.mlp if isinstance(m, nn.Linear)]
+            norm = bool(getattr(self, "normalize", False)) or isinstance(self.mlp[-1], L2NormalizationLayer)
+            return library.mlp(x.reshape(-1, self.input_dim), norm, weights).reshape(*x.shape[:-1], self.out_dim)
+        return self._forward_eager(x)
+
+    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
+    def _forward_eager(self, x: Tensor) -> Tensor:
         if self._bf16_wanted(x):
             weights = [m.weight for m in self.mlp if isinstance(m, nn.Linear)]
             lead = x.shape[:-1]

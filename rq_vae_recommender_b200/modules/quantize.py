@@ -111,7 +111,11 @@ class Quantize(nn.Module):
         w = self.embedding.weight
         for m in self.out_proj:
             if isinstance(m, nn.Linear):
-                w = ops.MLPFunction.apply(w, False, m.weight)
+                if torch.compiler.is_compiling():
+                    from .. import library
+                    w = library.mlp(w, False, [m.weight])
+                else:
+                    w = ops.MLPFunction.apply(w, False, m.weight)
             elif not isinstance(m, nn.Identity):
                 w = m(w)
         return w
@@ -132,8 +136,26 @@ class Quantize(nn.Module):
             return _KERNEL_MODE[self.forward_mode]
         raise Exception("Unsupported Quantize forward mode.")
 
-    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
     def forward(self, x, temperature) -> QuantizeOutput:
+        if (torch.compiler.is_compiling() and not (self.do_kmeans_init and not self.kmeans_initted)
+                and self.distance_mode == QuantizeDistance.L2):
+            # inside torch.compile: the level is one custom-operator node (library.py); the lazy k-means init is data dependent
+            # (host-side convergence check) and stays a graph break on the one call that runs it
+            from .. import library
+            codebook = self.codebook()
+            mode = self.kernel_mode()
+            beta = self.quantize_loss.commitment_weight
+            if mode == ops.MODE_GUMBEL:
+                uniform = _gumbel.draw_uniform((x.shape[0], self.n_embed), self.device)
+                emb_out, ids, loss = library.gumbel_level(x, codebook, uniform, temperature, beta)
+            else:
+                embs, _res, ids, loss = library.rq_chain(x, mode, beta, False, [codebook])
+                emb_out, ids = embs[0], ids[:, 0]
+            return QuantizeOutput(embeddings=emb_out, ids=ids, loss=loss)
+        return self._forward_eager(x, temperature)
+
+    @torch.compiler.disable      # ctypes call into librqb200: opaque to Dynamo
+    def _forward_eager(self, x, temperature) -> QuantizeOutput:
         assert x.shape[-1] == self.embed_dim
 
         if self.do_kmeans_init and not self.kmeans_initted:

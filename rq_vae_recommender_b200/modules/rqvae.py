@@ -153,13 +153,28 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
         return (not pending_init and len(modes) == 1 and ops.MODE_GUMBEL not in modes and len(betas) == 1
                 and len(self.layers) <= 8)
 
-    @torch.compiler.disable      # librqb200 is called through ctypes: opaque to Dynamo (a compiled caller breaks the graph HERE, cleanly)
     def _chain(self, res: Tensor, gumbel_t: float, lean: bool):
+        if torch.compiler.is_compiling():
+            # inside torch.compile (the reference compiles forward, rqvae.py:141): the kernels are custom-operator nodes of the
+            # captured graph (library.py); everything else in here is plain torch and Python that Dynamo traces
+            from .. import library
+            if self._fusable():
+                mode = self.layers[0].kernel_mode()
+                beta = self.layers[0].quantize_loss.commitment_weight
+                return library.rq_chain(res, mode, beta, lean, [layer.codebook() for layer in self.layers])
+            return self._chain_levels(res, gumbel_t, lean)
+        return self._chain_eager(res, gumbel_t, lean)
+
+    @torch.compiler.disable      # librqb200 is called through ctypes: opaque to Dynamo
+    def _chain_eager(self, res: Tensor, gumbel_t: float, lean: bool):
         if self._fusable():
             mode = self.layers[0].kernel_mode()
             beta = self.layers[0].quantize_loss.commitment_weight
             codebooks = [layer.codebook() for layer in self.layers]
             return ops.RqChainFunction.apply(res, mode, beta, lean, *codebooks)
+        return self._chain_levels(res, gumbel_t, lean)
+
+    def _chain_levels(self, res: Tensor, gumbel_t: float, lean: bool):
         # level-by-level (first call with k-means init pending, or GUMBEL_SOFTMAX training): rqvae.py:122-132
         quantize_loss = 0
         embs, residuals, sem_ids = [], [], []
@@ -223,7 +238,12 @@ class RqVae(nn.Module, PyTorchModelHubMixin):
 
         with torch.no_grad():
             # Compute debug ID statistics
-            p_unique_ids = (count_unique_id_tuples(sem_ids, self.codebook_size) / sem_ids.shape[0]).to(torch.float32)
+            if torch.compiler.is_compiling():
+                from .. import library
+                n_unique = library.count_unique_id_tuples(sem_ids, self.codebook_size)
+            else:
+                n_unique = count_unique_id_tuples(sem_ids, self.codebook_size)
+            p_unique_ids = (n_unique / sem_ids.shape[0]).to(torch.float32)
 
         return RqVaeComputedLosses(
             loss=loss,

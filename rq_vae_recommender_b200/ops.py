@@ -219,6 +219,9 @@ _SPLIT_CACHE_MAX = 32
 def split_operand_cached(t: torch.Tensor, transposed: bool = False) -> SplitOperand:
     # the entry remembers the tensor OBJECT (weak reference): a temporary that died and whose address the allocator handed to
     # another tensor of the same shape must not hit
+    if torch.cuda.is_current_stream_capturing():
+        return SplitOperand(t, transposed)       # inside a CUDA-graph capture the split kernel must be PART of the graph (replays
+                                                 # see the weights of that moment, not the images of capture time)
     key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index, bool(transposed))
     hit = _SPLIT_CACHE.get(key)
     if hit is not None and hit[0]() is t:
@@ -611,6 +614,8 @@ def _tc_cache_key(codebooks: Sequence[torch.Tensor]):
 def tc_state_for(codebooks: Sequence[torch.Tensor]) -> TcState:
     # an entry also remembers the tensor OBJECTS (weak references): a derived codebook (sim_vq projection, normalised rows) is a
     # temporary whose address the allocator may hand to the next call's temporary with the same version counter
+    if torch.cuda.is_current_stream_capturing():
+        return TcState(codebooks)                # a captured graph re-prepares on every replay (see split_operand_cached)
     key = _tc_cache_key(codebooks)
     hit = _TC_CACHE.get(key)
     if hit is not None and all(r() is c for r, c in zip(hit[0], codebooks)):

@@ -197,3 +197,26 @@ def test_sharded_kmeans_windowed_host_checks_equal_per_iteration_checks():
                                                 assign_accumulate=_cpu_assign_accumulate, finalize=_cpu_finalize, make_buf=_cpu_make_buf)
         res.append((cen.numpy(), iters))
     assert res[0][1] == res[1][1] and np.allclose(res[0][0], res[1][0], atol=1e-6)
+
+
+@pytest.mark.parametrize("mode_name,train", [("STE", True), ("ROTATION_TRICK", True), ("GUMBEL_SOFTMAX", True), ("STE", False)])
+def test_forward_traces_to_one_graph_of_custom_operators(mode_name, train):
+    """RqVae.forward (compiled by the reference, rqvae.py:141) exports as ONE graph (torch._dynamo.export raises on a
+    graph break) whose kernel calls are rqb200:: custom operators.  Fake tensors only: no kernel runs, CPU is enough."""
+    import torch
+    import rq_vae_recommender_b200.library  # noqa: F401  (registers the operators)
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode as M
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    m = RqVae(input_dim=64, embed_dim=16, hidden_dims=[32], codebook_size=32, codebook_kmeans_init=False,
+              codebook_mode=getattr(M, mode_name), n_layers=2, commitment_weight=0.25, n_cat_features=4)
+    m.train(train)
+
+    def f(x):
+        out = m(SeqBatch(None, None, None, x, None, None), 0.2)
+        return out.loss, out.p_unique_ids, out.embs_norm
+
+    gm = torch._dynamo.export(f)(torch.randn(48, 64)).graph_module
+    names = {str(n.target) for n in gm.graph.nodes if n.op == "call_function" and "rqb200" in str(n.target)}
+    level = "rqb200.gumbel_level_fwd.default" if (mode_name == "GUMBEL_SOFTMAX" and train) else "rqb200.rq_chain_fwd.default"
+    assert names == {"rqb200.mlp_fwd.default", "rqb200.l2norm_fwd.default", "rqb200.count_unique_id_tuples.default", level}, names

@@ -33,4 +33,13 @@ ops.sid_gather(torch.cat([ids3, rank.unsqueeze(1)], 1), torch.randint(0, 1000, (
 # tc tokeniser at both tile shapes: several tiles per CTA pair, ragged tail
 x, cbs = I.rq_problem(30000, 768, 256, 3, seed=12)
 ops.rq_tokenize_tc(dev(x[:777]), [dev(c) for c in cbs]); ops.rq_tokenize_tc(dev(x), [dev(c) for c in cbs])
+# split-precision GEMM: ragged M / N / K, transposed operand, mask; MLP forward + dgrad on it; Gumbel level on it
+a = dev(I.randn(20, 700, 100)); b = dev(I.randn(21, 200, 100)); bt = dev(I.randn(22, 100, 130))
+ops.gemm_split(a, b, relu=True); ops.gemm_split(a, ops.SplitOperand(bt, transposed=True), mask=dev(I.randn(23, 700, 130)))
+ws = [dev(w).requires_grad_(True) for w in I.mlp_weights(24, [72, 40, 24])]
+xm = dev(I.randn(25, 600, 72)).requires_grad_(True)
+ops.MLPFunction.apply(xm, True, *ws).sum().backward()
+x, cbs = I.rq_problem(640, 64, 256, 1, seed=26)
+xt = dev(x).requires_grad_(True); ct = dev(cbs[0]).requires_grad_(True)
+e, ids, loss = ops.GumbelQuantizeFunction.apply(xt, ct, dev(I.rand(27, 640, 256)), 0.2, 0.25); (e.sum() + loss.sum()).backward()
 torch.cuda.synchronize(); print("sanitize pass done")
