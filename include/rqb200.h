@@ -139,6 +139,12 @@ size_t rqb200_split_image_bytes(int rows, int K);
 int rqb200_f32_to_split_image(const float* x, int64_t ldx, int rows, int K, int transposed, void* image, void* stream);
 int rqb200_gemm_split(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask,
                       int64_t ldm, float* out, int64_t ldo, void* stream);
+/* split-K schedule for few output tiles and a long contraction (weight gradients, modules/encoder.py backward: M = out,
+ * N = in, K = batch): gemm_split_k_slices returns the slice count that fills the SMs; workspace = slices * M * N floats
+ * (unused when slices == 1); the partial sums are reduced in a fixed order. */
+int rqb200_gemm_split_k_slices(int M, int N, int K);
+int rqb200_gemm_split_k(const void* a_image, const void* b_image, int M, int N, int K, int slices, float* workspace,
+                        float* out, int64_t ldo, void* stream);
 
 /* ---- corpus id statistics (train_rqvae.py:279-289, modules/tokenizer/semids.py:94-108) ---------------- */
 int rqb200_sid_histogram(const int64_t* ids, int B, int L, int K, int64_t* hist /* [L,K], zeroed here */,

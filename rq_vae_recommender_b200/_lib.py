@@ -67,6 +67,8 @@ _SIGNATURES = {
     "rqb200_split_image_bytes": (c_size, [c_int, c_int]),
     "rqb200_f32_to_split_image": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
     "rqb200_gemm_split": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "rqb200_gemm_split_k_slices": (c_int, [c_int, c_int, c_int]),
+    "rqb200_gemm_split_k": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),
 }
 
 

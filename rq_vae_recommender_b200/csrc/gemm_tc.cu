@@ -401,31 +401,51 @@ __global__ void __launch_bounds__(256) gs_split_rows_kernel(const float* __restr
   }
 }
 
-// Transposed source: image row r = column r of x[K, rows] (ld = ldx).  One thread per image row (reads of a k are coalesced
-// across the 128 threads of the tile), two passes over the column: maximum, then split.  grid = row tiles, block = 128.
-__global__ void gs_split_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, unsigned char* img) {
-  const int nkc = (K + GT_KC - 1) / GT_KC, mtiles = gridDim.x;
-  const int mt = blockIdx.x, r = threadIdx.x;
+// Transposed source: image row r = column r of x[K, rows] (ld = ldx) -- the operand of x^T without materialising the transpose
+// (W^T for dgrad, C^T for W@C, g^T and h^T for the weight gradients whose contraction runs over the batch).  Three launches:
+//   gs_colmax_kernel    |column| maxima by atomicMax on the float bits (non-negative floats order like unsigned ints) into scales[]
+//   gs_colscale_kernel  scales[r] = 2^-e
+//   gs_split_cols_kernel one CTA per (row tile, k chunk): 64 x 128 source floats through shared memory (coalesced reads, the
+//                       transposed reads are conflict-free with a 129-float pitch), hi / lo blocks written as 16-byte chunks
+__global__ void gs_colmax_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, unsigned int* colmax) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.y * 128;
+  if (c >= rows) return;
+  float mx = 0.f;
+  const int k1 = min(K, k0 + 128);
+  for (int k = k0; k < k1; ++k) mx = fmaxf(mx, fabsf(__ldg(x + (int64_t)k * ldx + c)));
+  if (mx != mx) mx = INFINITY;                               // NaN: not scaled (gs_pow2_scale), like the row kernel
+  atomicMax(colmax + c, __float_as_uint(mx));
+}
+__global__ void gs_colscale_kernel(float* scales, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scales[i] = 1.f / gs_pow2_scale(scales[i]);
+}
+__global__ void __launch_bounds__(256) gs_split_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int K, unsigned char* img) {
+  __shared__ float tile[GT_KC][129];
+  const int mtiles = gridDim.x, nkc = gridDim.y;
+  const int mt = blockIdx.x, kc = blockIdx.y, t = threadIdx.x;
   unsigned char* hi_img = img;
   unsigned char* lo_img = img + (size_t)mtiles * nkc * GT_BLK_BYTES;
-  float* scales = reinterpret_cast<float*>(img + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
-  const int row = mt * 128 + r;
-  const bool live = row < rows;
-  float mx = 0.f;
-  if (live)
-    for (int k = 0; k < K; ++k) mx = fmaxf(mx, fabsf(__ldg(x + (int64_t)k * ldx + row)));
-  const float s = gs_pow2_scale(mx);
-  scales[row] = 1.f / s;
-  for (int c = 0; c < nkc * 8; ++c) {
+  const float* scales = reinterpret_cast<const float*>(img + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
+#pragma unroll 4
+  for (int i = 0; i < (GT_KC * 128) / 256; ++i) {
+    const int idx = t + 256 * i, kr = idx >> 7, c = idx & 127;
+    const int k = kc * GT_KC + kr, row = mt * 128 + c;
+    tile[kr][c] = (k < K && row < rows) ? __ldg(x + (int64_t)k * ldx + row) : 0.f;
+  }
+  __syncthreads();
+  const int r = t & 127;
+  const float s = 1.f / scales[mt * 128 + r];                 // exact: a power of two
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = (t >> 7) * 4 + cc;                          // 16-byte chunk of the 128-byte block row
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = c * 8 + e;
-      v[e] = (live && k < K) ? __ldg(x + (int64_t)k * ldx + row) : 0.f;
-    }
+    for (int e = 0; e < 8; ++e) v[e] = tile[c * 8 + e][r];
     uint4 hi, lo;
     gs_split8(v, s, hi, lo);
-    const size_t off = ((size_t)mt * nkc + (c >> 3)) * GT_BLK_BYTES + r * 128 + (((c & 7) ^ (r & 7)) << 4);
+    const size_t off = ((size_t)mt * nkc + kc) * GT_BLK_BYTES + r * 128 + ((c ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(hi_img + off) = hi;
     *reinterpret_cast<uint4*>(lo_img + off) = lo;
   }
@@ -440,7 +460,15 @@ extern "C" int rqb200_f32_to_split_image(const float* x, int64_t ldx, int rows, 
   const int mtiles = (rows + 127) / 128;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (transposed) {
-    gs_split_cols_kernel<<<mtiles, 128, 0, st>>>(x, ldx, rows, K, reinterpret_cast<unsigned char*>(image));
+    unsigned char* im = reinterpret_cast<unsigned char*>(image);
+    const int nkc = (K + GT_KC - 1) / GT_KC;
+    float* scales = reinterpret_cast<float*>(im + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
+    RQB_CUDA(cudaMemsetAsync(scales, 0, (size_t)mtiles * 128 * sizeof(float), st));
+    gs_colmax_kernel<<<dim3((rows + 255) / 256, (K + 127) / 128), 256, 0, st>>>(x, ldx, rows, K, reinterpret_cast<unsigned int*>(scales));
+    RQB_LAUNCH_CHECK();
+    gs_colscale_kernel<<<(mtiles * 128 + 255) / 256, 256, 0, st>>>(scales, mtiles * 128);
+    RQB_LAUNCH_CHECK();
+    gs_split_cols_kernel<<<dim3(mtiles, nkc), 256, 0, st>>>(x, ldx, rows, K, im);
   } else {
     if (K > 32 * 8 * GS_MAX_CHUNKS) {
       rqb_set_error("f32_to_split_image: K = %d > %d", K, 32 * 8 * GS_MAX_CHUNKS);
@@ -464,6 +492,8 @@ struct GsParams {
   const unsigned char *a_hi, *a_lo, *b_hi, *b_lo;   // [tiles][nkc][16 KB]
   const float *a_scale, *b_scale;                   // 2^-e per image row
   int M, N, nkc, mtiles, nblocks, ngroups, nitems, relu;
+  int ksplit, kc_per;                               // split-K: item = (row tile, column group, k slice of kc_per chunks); slice ks
+  int64_t part_stride;                              // writes its partial sums to out + ks * part_stride (ksplit == 1: 0)
   float* out;
   int64_t ldo;
   const float* mask;                                // optional [M, N] (ld = ldm): out = mask > 0 ? out : 0  (ReLU' of a backward GEMM)
@@ -497,9 +527,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
     // ============================================================== producer: 2 A blocks + 2 or 4 B blocks per stage
     uint32_t s = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      const int mt = item / p.ngroups, g = item % p.ngroups;
+      const int ks = item % p.ksplit, tile = item / p.ksplit;
+      const int mt = tile / p.ngroups, g = tile % p.ngroups;
       const int nb = min(2, p.nblocks - 2 * g);
-      for (int kc = 0; kc < p.nkc; ++kc, ++s) {
+      const int kc_end = min(p.nkc, (ks + 1) * p.kc_per);
+      for (int kc = ks * p.kc_per; kc < kc_end; ++kc, ++s) {
         const uint32_t st = s % GS_STAGES, u = s / GS_STAGES;
         mbar_wait_guarded(&ms->empty[st], (u & 1) ^ 1, 1);
         unsigned char* dst = gsm + st * GS_STAGE_BYTES;
@@ -519,9 +551,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
     const uint32_t base = smem_u32(gsm);
     uint32_t s = 0, it = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
-      const int g = item % p.ngroups;
+      const int ks = item % p.ksplit, g = (item / p.ksplit) % p.ngroups;
       const int nb = min(2, p.nblocks - 2 * g);
       const uint32_t idesc = gs_idesc_f16(128, nb * 128);
+      const int kc_begin = ks * p.kc_per, kc_end = min(p.nkc, (ks + 1) * p.kc_per);
       mbar_wait_guarded(&ms->t_empty[0], (it & 1) ^ 1, 2);
       gt_fence_after();
       // two accumulators: hi.hi in columns [0, 256), the cross terms in [256, 512).  The tensor core truncates the fp32
@@ -529,7 +562,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
       // round-toward-zero model, 5.4e-7 of |a||b| at K = 768); apart, the large sum sees a third of the truncations and the
       // small one truncates at 2^-11 of the magnitude: 1.8e-7, the level of a plain fp32 GEMM
       const uint32_t d = GT_TMEM(), dx = GT_TMEM() + 256;
-      for (int kc = 0; kc < p.nkc; ++kc, ++s) {
+      for (int kc = kc_begin; kc < kc_end; ++kc, ++s) {
         const uint32_t st = s % GS_STAGES;
         mbar_wait_guarded(&ms->full[st], (s / GS_STAGES) & 1, 3);
         gt_fence_after();
@@ -538,8 +571,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
         const uint64_t bhi = gt_smem_desc(sa + 2 * GT_BLK_BYTES), blo = gt_smem_desc(sa + 4 * GT_BLK_BYTES);
 #pragma unroll
         for (int j = 0; j < GT_KC / 16; ++j) {
-          gt_mma(d, ahi + 2 * j, bhi + 2 * j, idesc, (kc | j) != 0);
-          gt_mma(dx, alo + 2 * j, bhi + 2 * j, idesc, (kc | j) != 0);
+          gt_mma(d, ahi + 2 * j, bhi + 2 * j, idesc, ((kc - kc_begin) | j) != 0);
+          gt_mma(dx, alo + 2 * j, bhi + 2 * j, idesc, ((kc - kc_begin) | j) != 0);
           gt_mma(dx, ahi + 2 * j, blo + 2 * j, idesc, 1);
         }
         gt_commit(&ms->empty[st]);
@@ -554,7 +587,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
-      const int mt = item / p.ngroups, g = item % p.ngroups;
+      const int ks = item % p.ksplit, tile = item / p.ksplit;
+      const int mt = tile / p.ngroups, g = tile % p.ngroups;
       const int nb = min(2, p.nblocks - 2 * g);
       mbar_wait_guarded(&ms->t_full[0][blk], it & 1, 4);
       gt_fence_after();
@@ -590,7 +624,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
               if (col + e < p.N && !(__ldg(mk + e) > 0.f)) v[e] = 0.f;
           }
           if (row < p.M) {
-            float* o = p.out + (int64_t)row * p.ldo + col;
+            float* o = p.out + (int64_t)ks * p.part_stride + (int64_t)row * p.ldo + col;
             if (col + 32 <= p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(o + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
@@ -615,18 +649,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gs_gemm_kernel(GsParams p) {
   }
 }
 
-extern "C" int rqb200_gemm_split(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask,
-                                 int64_t ldm, float* out, int64_t ldo, void* stream) {
-  RQB_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldo >= N, "gemm_split: bad shape (M=%d N=%d K=%d ldo=%lld)", M, N, K, (long long)ldo);
-  if (M == 0) return RQB_OK;
-  RQB_CHECK_ARG(a_image && b_image && out, "gemm_split: null pointer");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// out[i, j] = sum over the k slices of the partial sums (fixed order: deterministic)
+__global__ void gs_reduce_kernel(const float* __restrict__ part, int S, int M, int N, float* __restrict__ out, int64_t ldo) {
+  const int64_t n = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += part[(int64_t)s * n + i];
+    out[(i / N) * ldo + (i % N)] = acc;
+  }
+}
+
+static int gs_run(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask, int64_t ldm,
+                  float* out, int64_t ldo, int ksplit, int kc_per, int64_t part_stride, cudaStream_t st) {
   GsParams p{};
   p.M = M; p.N = N; p.nkc = (K + GT_KC - 1) / GT_KC;
   p.mtiles = (M + 127) / 128;
   p.nblocks = (N + 127) / 128;
   p.ngroups = (p.nblocks + 1) / 2;
-  p.nitems = p.mtiles * p.ngroups;
+  p.ksplit = ksplit; p.kc_per = kc_per; p.part_stride = part_stride;
+  p.nitems = p.mtiles * p.ngroups * ksplit;
   p.relu = relu;
   const size_t a_img = (size_t)p.mtiles * p.nkc * GT_BLK_BYTES, b_img = (size_t)p.nblocks * p.nkc * GT_BLK_BYTES;
   p.a_hi = reinterpret_cast<const unsigned char*>(a_image); p.a_lo = p.a_hi + a_img;
@@ -635,7 +676,6 @@ extern "C" int rqb200_gemm_split(const void* a_image, const void* b_image, int M
   p.b_scale = reinterpret_cast<const float*>(p.b_hi + 2 * b_img);
   p.out = out; p.ldo = ldo;
   p.mask = mask; p.ldm = ldm;
-  RQB_CHECK_ARG(!mask || ldm >= N, "gemm_split: ldm < N");
   int dev = 0, sm_count = 0;
   RQB_CUDA(cudaGetDevice(&dev));
   RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -643,6 +683,53 @@ extern "C" int rqb200_gemm_split(const void* a_image, const void* b_image, int M
   RQB_CUDA(cudaFuncSetAttribute(gs_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.nitems < sm_count ? p.nitems : sm_count;
   gs_gemm_kernel<<<grid, GT_THREADS, smem, st>>>(p);
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
+}
+
+extern "C" int rqb200_gemm_split(const void* a_image, const void* b_image, int M, int N, int K, int relu, const float* mask,
+                                 int64_t ldm, float* out, int64_t ldo, void* stream) {
+  RQB_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldo >= N, "gemm_split: bad shape (M=%d N=%d K=%d ldo=%lld)", M, N, K, (long long)ldo);
+  if (M == 0) return RQB_OK;
+  RQB_CHECK_ARG(a_image && b_image && out, "gemm_split: null pointer");
+  RQB_CHECK_ARG(!mask || ldm >= N, "gemm_split: ldm < N");
+  return gs_run(a_image, b_image, M, N, K, relu, mask, ldm, out, ldo, 1, (K + GT_KC - 1) / GT_KC, 0,
+                reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Split-K schedule for products with few output tiles and a long contraction (the weight gradients: M = out, N = in, K = batch):
+// the k chunks are cut into `slices` ranges, every (tile, range) is a work item writing partial sums into the workspace
+// [slices][M][N], and a fixed-order reduction produces out.  gemm_split_k_slices picks the slice count that fills the SMs.
+extern "C" int rqb200_gemm_split_k_slices(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  int dev = 0, sm_count = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int nkc = (K + GT_KC - 1) / GT_KC;
+  const int tiles = ((M + 127) / 128) * (((N + 127) / 128 + 1) / 2);
+  int want = (sm_count + tiles - 1) / tiles;                 // slices that give every SM an item
+  if (want > nkc / 4) want = nkc / 4;                        // at least 4 chunks (256 k) per slice
+  if (want < 1) want = 1;
+  const int kc_per = (nkc + want - 1) / want;
+  return (nkc + kc_per - 1) / kc_per;                        // no empty slice
+}
+
+extern "C" int rqb200_gemm_split_k(const void* a_image, const void* b_image, int M, int N, int K, int slices, float* workspace,
+                                   float* out, int64_t ldo, void* stream) {
+  RQB_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldo >= N && slices >= 1, "gemm_split_k: bad shape (M=%d N=%d K=%d slices=%d)", M, N, K, slices);
+  if (M == 0) return RQB_OK;
+  RQB_CHECK_ARG(a_image && b_image && out, "gemm_split_k: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nkc = (K + GT_KC - 1) / GT_KC;
+  const int kc_per = (nkc + slices - 1) / slices;
+  RQB_CHECK_ARG((int64_t)(slices - 1) * kc_per < nkc, "gemm_split_k: %d slices of %d chunks leave an empty slice (K = %d)", slices, kc_per, K);
+  if (slices == 1) return gs_run(a_image, b_image, M, N, K, 0, nullptr, 0, out, ldo, 1, nkc, 0, st);
+  RQB_CHECK_ARG(workspace, "gemm_split_k: null workspace");
+  int rc = gs_run(a_image, b_image, M, N, K, 0, nullptr, 0, workspace, N, slices, kc_per, (int64_t)M * N, st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)M * N;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  gs_reduce_kernel<<<grid, 256, 0, st>>>(workspace, slices, M, N, out, ldo);
   RQB_LAUNCH_CHECK();
   return RQB_OK;
 }

@@ -46,7 +46,8 @@ def _fresh(t: Tensor, *inputs: Tensor) -> Tensor:
 def mlp_fwd(x: Tensor, normalize: bool, weights: Sequence[Tensor]) -> List[Tensor]:
     """[activations of every layer (the last one is the output), row norms when normalize] -- modules/encoder.py:23-38"""
     ctx = _Ctx()
-    ops.MLPFunction.forward(ctx, x, normalize, *weights)
+    with ops.no_operand_cache():
+        ops.MLPFunction.forward(ctx, x, normalize, *weights)
     n = len(weights)
     n_act = n + 1 + (1 if normalize else 0)
     acts = ctx.saved_tensors[1:n_act]                       # acts[0] is the input itself
@@ -74,7 +75,8 @@ def mlp_bwd(g: Tensor, x: Tensor, normalize: bool, weights: Sequence[Tensor], sa
     ws = [ops._f32c(w) for w in weights]
     acts = [x2, *saved[:n + (1 if normalize else 0)]]
     ctx.saved_tensors = (*acts, *ws, *([saved[-1]] if normalize else []))
-    gx, _none, *gws = ops.MLPFunction.backward(ctx, g)
+    with ops.no_operand_cache():
+        gx, _none, *gws = ops.MLPFunction.backward(ctx, g)
     out = [gx if gx is not None else x.new_zeros(x.shape, dtype=torch.float32)]
     out += [gw if gw is not None else w.new_zeros(w.shape, dtype=torch.float32) for gw, w in zip(gws, weights)]
     return [_fresh(t, g, x, *weights, *saved) for t in out]
@@ -179,7 +181,8 @@ def rq_chain(x: Tensor, mode: int, beta: float, lean: bool, codebooks: Sequence[
 def gumbel_level_fwd(x: Tensor, codebook: Tensor, uniform: Tensor, temperature: float, beta: float) -> List[Tensor]:
     """[emb, ids, loss, softmax weights (saved for the backward)] -- modules/quantize.py:113-136"""
     ctx = _Ctx()
-    emb, ids, loss = ops.GumbelQuantizeFunction.forward(ctx, x, codebook, uniform, temperature, beta)
+    with ops.no_operand_cache():
+        emb, ids, loss = ops.GumbelQuantizeFunction.forward(ctx, x, codebook, uniform, temperature, beta)
     return [emb, ids, loss, ctx.saved_tensors[2]]
 
 
@@ -197,7 +200,8 @@ def gumbel_level_bwd(g_emb: Optional[Tensor], g_loss: Optional[Tensor], x: Tenso
     ctx = _Ctx((True, True, False, False, False))
     ctx.temperature, ctx.beta = temperature, beta
     ctx.saved_tensors = (ops._rows(x), ops._f32c(codebook), w, emb)
-    gx, gc, *_ = ops.GumbelQuantizeFunction.backward(ctx, g_emb, None, g_loss)
+    with ops.no_operand_cache():
+        gx, gc, *_ = ops.GumbelQuantizeFunction.backward(ctx, g_emb, None, g_loss)
     return [gx, gc]
 
 

@@ -216,10 +216,27 @@ _SPLIT_CACHE: "dict[tuple, tuple]" = {}
 _SPLIT_CACHE_MAX = 32
 
 
+_NO_OPERAND_CACHE = 0
+
+
+class no_operand_cache:
+    """Inside this context prepared operands are rebuilt on every use and never stored.  The torch.library operators run under
+    it: a compiled caller (mode="reduce-overhead") executes them inside a CUDA-graph memory pool -- warm-up run included -- where
+    a cached buffer would be an allocation the graph does not own, and a replay must see the weights of that moment."""
+
+    def __enter__(self):
+        global _NO_OPERAND_CACHE
+        _NO_OPERAND_CACHE += 1
+
+    def __exit__(self, *a):
+        global _NO_OPERAND_CACHE
+        _NO_OPERAND_CACHE -= 1
+
+
 def split_operand_cached(t: torch.Tensor, transposed: bool = False) -> SplitOperand:
     # the entry remembers the tensor OBJECT (weak reference): a temporary that died and whose address the allocator handed to
     # another tensor of the same shape must not hit
-    if torch.cuda.is_current_stream_capturing():
+    if _NO_OPERAND_CACHE or torch.cuda.is_current_stream_capturing():
         return SplitOperand(t, transposed)       # inside a CUDA-graph capture the split kernel must be PART of the graph (replays
                                                  # see the weights of that moment, not the images of capture time)
     key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.device.index, bool(transposed))
@@ -254,6 +271,28 @@ def gemm_split(a, b, *, relu: bool = False, mask: Optional[torch.Tensor] = None,
                                          mask.stride(0) if mask is not None else 0, _p(out), out.stride(0), _stream()),
                    "gemm_split")
     _count(1)
+    SPLIT_CALLS += 1
+    return out
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T @ b for a [B, M], b [B, N]: the contraction runs over the (long) batch dimension -- weight / codebook gradients.
+    Tensor cores with a split-K schedule from SPLIT_MIN_ROWS batch rows on (both operands are split transposed, partial sums are
+    reduced in a fixed order), the CUDA-core SGEMM below."""
+    global SPLIT_CALLS
+    B = a.shape[0]
+    if B < SPLIT_MIN_ROWS:
+        return sgemm(a, b, trans_a=True)
+    lib = _lib.load()
+    ao, bo = SplitOperand(a, transposed=True), SplitOperand(b, transposed=True)
+    M, N = ao.rows, bo.rows
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        slices = lib.rqb200_gemm_split_k_slices(M, N, B)
+        ws = torch.empty((slices, M, N), dtype=torch.float32, device=a.device) if slices > 1 else None
+        _lib.check(lib.rqb200_gemm_split_k(_p(ao.buf), _p(bo.buf), M, N, B, slices, _p(ws), _p(out), out.stride(0), _stream()),
+                   "gemm_split_k")
+    _count(2 if slices > 1 else 1)
     SPLIT_CALLS += 1
     return out
 
@@ -317,7 +356,7 @@ class MLPFunction(torch.autograd.Function):
         for i in range(n - 1, -1, -1):
             h_in = acts[i]
             if ctx.needs_input_grad[2 + i]:
-                g_ws[i] = sgemm(g, h_in, trans_a=True)                     # [out,B] @ [B,in]
+                g_ws[i] = gemm_tn(g, h_in)                                 # [out,B] @ [B,in]
             if i > 0 or ctx.needs_input_grad[0]:
                 g = linear_nt(g, ws[i], mask=h_in if i > 0 else None, w_transposed=True)   # [B,out] @ [out,in], ReLU' of layer i-1
         return (g if ctx.needs_input_grad[0] else None, None, *g_ws)
@@ -423,8 +462,12 @@ class GumbelQuantizeFunction(torch.autograd.Function):
                                                 ctx.beta, B, D, st), "bwd_gx")
             gc = None
             if ctx.needs_input_grad[1]:
-                gc = sgemm(w, gE, trans_a=True)                                  # W^T @ gE        [K,D]
-                sgemm(gw, x, trans_a=True, out=gc, alpha=-2.0, beta=1.0)         # - 2 gdist^T @ x
+                if B >= SPLIT_MIN_ROWS:
+                    gc = gemm_tn(w, gE)                                          # W^T @ gE        [K,D]
+                    gc.add_(gemm_tn(gw, x), alpha=-2.0)                          # - 2 gdist^T @ x
+                else:
+                    gc = sgemm(w, gE, trans_a=True)
+                    sgemm(gw, x, trans_a=True, out=gc, alpha=-2.0, beta=1.0)
                 _lib.check(lib.rqb200_gumbel_bwd_gc(_p(gc), _p(cb), _p(colsum), K, D, st), "bwd_gc")
         _count(5)
         return (gx if ctx.needs_input_grad[0] else None, gc, None, None, None)
@@ -614,7 +657,7 @@ def _tc_cache_key(codebooks: Sequence[torch.Tensor]):
 def tc_state_for(codebooks: Sequence[torch.Tensor]) -> TcState:
     # an entry also remembers the tensor OBJECTS (weak references): a derived codebook (sim_vq projection, normalised rows) is a
     # temporary whose address the allocator may hand to the next call's temporary with the same version counter
-    if torch.cuda.is_current_stream_capturing():
+    if _NO_OPERAND_CACHE or torch.cuda.is_current_stream_capturing():
         return TcState(codebooks)                # a captured graph re-prepares on every replay (see split_operand_cached)
     key = _tc_cache_key(codebooks)
     hit = _TC_CACHE.get(key)

@@ -82,6 +82,22 @@ def test_gemm_split_extreme_rows():
     assert (out[0] == 0).all() and (out[:, 7] == 0).all()
 
 
+@pytest.mark.parametrize("B,M,N", [(4096, 512, 768), (1000, 32, 128), (70000, 256, 768), (513, 130, 70)])
+def test_gemm_tn_split_k_matches_float64(B, M, N):
+    """a^T @ b with the contraction over the batch (weight gradients): transposed split of both operands + split-K."""
+    from rq_vae_recommender_b200 import ops
+    a = dev(I.randn(570, B, M) * np.exp(0.5 * I.randn(571, 1, M)).astype(np.float32))     # columns of different scales
+    b = dev(I.randn(572, B, N) * 0.05)
+    out = ops.gemm_tn(a, b)
+    ref = a.double().t() @ b.double()
+    scale = a.double().norm(dim=0)[:, None] * b.double().norm(dim=0)[None, :]
+    e_tc = ((out.double() - ref).abs() / scale).max().item()
+    e_32 = (((a.t() @ b).double() - ref).abs() / scale).max().item()
+    print(f"B={B} M={M} N={N}: split-K GEMM error {e_tc:.3e}, fp32 GEMM error {e_32:.3e} (relative to |a_col||b_col|)")
+    assert e_tc <= max(2.0 * e_32, 3e-7), (e_tc, e_32)
+    assert torch.equal(out, ops.gemm_tn(a, b)), "fixed-order reduction: run-to-run identical"
+
+
 def _mlp_ref64(x, ws, normalize=False):
     h = x.double()
     for i, w in enumerate(ws):
@@ -105,7 +121,7 @@ def test_mlp_on_tensor_cores_forward_and_backward_vs_float64():
     calls0 = ops.SPLIT_CALLS
     y = ops.MLPFunction.apply(x, False, *ws)
     y.backward(gy)
-    assert ops.SPLIT_CALLS - calls0 == 2 * len(ws), "forward + dgrad of every layer must run on the tensor-core GEMM"
+    assert ops.SPLIT_CALLS - calls0 == 3 * len(ws), "forward, dgrad and wgrad of every layer must run on the tensor-core GEMM"
     got = [y.detach()] + [x.grad] + [w.grad for w in ws]
 
     def run(dtype):
@@ -125,7 +141,7 @@ def test_mlp_on_tensor_cores_forward_and_backward_vs_float64():
         e_tc = (g.double() - r64).abs().max().item() / den
         e_32 = (r32.double() - r64).abs().max().item() / den
         print(f"MLP {name}: tensor-core path {e_tc:.3e}, fp32 torch {e_32:.3e} (max abs error / max |f64|)")
-        # (gw*: the weight gradients are the CUDA-core SGEMM over the batch dimension fed by the tensor-core dgrad)
+        # (gw*: split-K over the batch dimension, partial sums reduced in a fixed order)
         assert e_tc <= max(4.0 * e_32, 3e-6), f"{name}: tensor-core path {e_tc:.3e} vs fp32 torch {e_32:.3e} (relative to max)"
         # (the gradients pass through ReLU masks: a pre-activation within rounding of zero flips a whole mask entry, in fp32
         # torch as well -- only the forward output has an absolute bar)

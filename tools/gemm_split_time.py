@@ -33,3 +33,14 @@ x = torch.randn(M, 768, device="cuda") * 0.05; cb = torch.randn(256, 768, device
 xo, co, cto = ops.SplitOperand(x), ops.SplitOperand(cb), ops.SplitOperand(cb, transposed=True)
 w = torch.rand(M, 256, device="cuda")
 print(f"dist GEMM {timeit(lambda: ops.gemm_split(xo, co))*1e3:.1f} us, split W {timeit(lambda: ops.SplitOperand(w))*1e3:.1f} us, W@C {timeit(lambda: ops.gemm_split(ops.SplitOperand(w), cto))*1e3:.1f} us")
+# full encoder forward + backward (dgrad + split-K wgrad on the tensor cores) at 65 536 rows
+xg = (torch.randn(M, 768, device="cuda") * 0.05).requires_grad_(True)
+wsg = [torch.from_numpy(w).cuda().requires_grad_(True) for w in I.mlp_weights(2, dims)]
+def fb():
+    y = ops.MLPFunction.apply(xg, False, *wsg)
+    y.backward(torch.ones_like(y))
+print(f"encoder forward + backward at {M} rows: {timeit(fb, n=5)*1e3:.1f} us", flush=True)
+for (Bb, Mo, Ni) in [(65536, 512, 768), (65536, 256, 512), (4096, 512, 768)]:
+    ga, hb = torch.randn(Bb, Mo, device="cuda"), torch.randn(Bb, Ni, device="cuda")
+    print(f"wgrad {Mo}x{Ni} over {Bb} rows: split-K tensor cores {timeit(lambda: ops.gemm_tn(ga, hb), n=5)*1e3:.1f} us, "
+          f"CUDA-core SGEMM {timeit(lambda: ops.sgemm(ga, hb, trans_a=True), n=2, ) *1e3:.1f} us", flush=True)

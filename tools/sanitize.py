@@ -36,6 +36,7 @@ ops.rq_tokenize_tc(dev(x[:777]), [dev(c) for c in cbs]); ops.rq_tokenize_tc(dev(
 # split-precision GEMM: ragged M / N / K, transposed operand, mask; MLP forward + dgrad on it; Gumbel level on it
 a = dev(I.randn(20, 700, 100)); b = dev(I.randn(21, 200, 100)); bt = dev(I.randn(22, 100, 130))
 ops.gemm_split(a, b, relu=True); ops.gemm_split(a, ops.SplitOperand(bt, transposed=True), mask=dev(I.randn(23, 700, 130)))
+ops.gemm_tn(dev(I.randn(28, 700, 130)), dev(I.randn(29, 700, 75)))          # transposed splits + split-K + reduce
 ws = [dev(w).requires_grad_(True) for w in I.mlp_weights(24, [72, 40, 24])]
 xm = dev(I.randn(25, 600, 72)).requires_grad_(True)
 ops.MLPFunction.apply(xm, True, *ws).sum().backward()
