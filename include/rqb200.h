@@ -166,6 +166,23 @@ int rqb200_sid_gather(const int64_t* cached_ids, int64_t n_corpus, int C, const 
                       const unsigned char* seq_mask, int64_t mask_stride, int B, int S, int64_t* out /* [B, S*C] */,
                       int64_t* token_type /* [B, S*C] or null */, void* stream);
 
+/* ---- constrained beam search, data side (modules/model.py:169-182 `_check_valid_prefix`, :340-376 the selection step) ----
+ * sid_prefix_build  : corpus id table [N, C] -> one bitmap per prefix length (workspace layout: levels 1..C, 256-byte aligned
+ *                     regions; sid_prefix_workspace_bytes returns 0 when K^C exceeds 2^33 bits)
+ * sid_prefix_check  : valid[p] = some corpus row starts with prefix[p, :l]   (one bit test instead of the reference's
+ *                     O(P N l) compare)
+ * sid_beam_select   : one launch per hierarchy level h: score kp x nc candidate extensions per batch row (sampled token
+ *                     log-probability + parent beam log-probability, -inf when the extended prefix is not in the corpus), keep
+ *                     the k best in descending order, gather their ids into out_generated [B, k, h + 1] and return the parent
+ *                     beam's global index b * kp + beam (the key/value-cache reorder index). */
+size_t rqb200_sid_prefix_workspace_bytes(int C, int K);
+int rqb200_sid_prefix_build(const int64_t* cached_ids, int64_t N, int C, int K, void* workspace, size_t ws_bytes, void* stream);
+int rqb200_sid_prefix_check(const int64_t* prefix, int64_t row_stride, int64_t P, int l, int C, int K, const void* workspace,
+                            unsigned char* valid, void* stream);
+int rqb200_sid_beam_select(const int64_t* samples, const float* samp_log_p, const int64_t* generated, const float* log_probas,
+                           int B, int kp, int nc, int h, int k, int C, int K, const void* prefix_workspace,
+                           int64_t* out_generated, float* out_log_probas, int64_t* out_parent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

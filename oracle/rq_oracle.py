@@ -373,3 +373,46 @@ def mlp_forward_bf16(x: np.ndarray, weights: Sequence[np.ndarray], normalize: bo
         else:
             h = y
     return l2norm(h) if normalize else h
+
+
+def check_valid_prefix(corpus_ids: np.ndarray, prefix: np.ndarray) -> np.ndarray:
+    """modules/model.py:169-182 `_check_valid_prefix`: bool [P], prefix p occurs as the first l ids of some corpus row."""
+    trimmed = corpus_ids[:, : prefix.shape[1]]
+    l = prefix.shape[1]
+    if trimmed.size * prefix.shape[0] > (1 << 26) and l <= 4 and trimmed.min(initial=0) >= 0 and trimmed.max(initial=0) < (1 << 15):
+        # large cases: the same predicate through packed keys (row equality <=> key equality for ids in [0, 2^15)); a prefix
+        # holding an id outside that range equals no corpus row
+        inside = ((prefix >= 0) & (prefix < (1 << 15))).all(axis=1)
+        w = (1 << 15) ** np.arange(l - 1, -1, -1, dtype=np.int64)
+        keys = (np.where(inside[:, None], prefix, 0).astype(np.int64) * w).sum(axis=1)
+        return inside & np.isin(keys, np.unique((trimmed.astype(np.int64) * w).sum(axis=1)))
+    out = np.zeros(prefix.shape[0], dtype=bool)
+    for i in range(0, prefix.shape[0], 4096):
+        batch = prefix[i:i + 4096]
+        out[i:i + 4096] = (trimmed[:, None, :] == batch[None, :, :]).all(axis=2).any(axis=0)
+    return out
+
+
+def beam_select(corpus_ids, samples, samp_log_p, generated, log_probas, k):
+    """One selection step of the constrained beam search, modules/model.py:353-388 (numpy restatement; stable sort, so equal
+    scores keep candidate order -- torch.sort there is unstable: compare ids only where the k-th score is not tied).
+    samples / samp_log_p [B * kp, nc]; generated [B, kp, h] or None; log_probas [B, kp] or None."""
+    nc = samples.shape[1]
+    if generated is None:
+        B = samples.shape[0]
+        valid = check_valid_prefix(corpus_ids, samples.reshape(-1, 1)).reshape(B, nc)
+        scores = np.where(valid, samp_log_p, -np.inf)
+        idx = np.argsort(-scores, axis=1, kind="stable")[:, :k]
+        gen = np.take_along_axis(samples, idx, 1)[:, :, None]
+        return gen, np.take_along_axis(scores, idx, 1), np.zeros((B, k), dtype=np.int64) + np.arange(B)[:, None]
+    B, kp, h = generated.shape
+    prev = np.repeat(generated.reshape(-1, h), nc, axis=0)
+    prefix = np.concatenate([prev, samples.reshape(-1, 1)], axis=1)
+    valid = check_valid_prefix(corpus_ids, prefix).reshape(B, kp * nc)
+    scores = np.where(valid, samp_log_p.reshape(B, kp * nc) + np.repeat(log_probas, nc, axis=1), -np.inf)
+    idx = np.argsort(-scores, axis=1, kind="stable")[:, :k]
+    parent = idx // nc
+    parent_ids = np.take_along_axis(generated, parent[:, :, None].repeat(h, 2), 1)
+    new_ids = np.take_along_axis(samples.reshape(B, kp * nc), idx, 1)[:, :, None]
+    return (np.concatenate([parent_ids, new_ids], axis=2), np.take_along_axis(scores, idx, 1),
+            parent + np.arange(B)[:, None] * kp)

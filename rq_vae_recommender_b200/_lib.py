@@ -61,6 +61,11 @@ _SIGNATURES = {
     "rqb200_sid_dedup_workspace_bytes": (c_size, [c_int, c_int, c_int]),
     "rqb200_sid_dedup_rank": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "rqb200_sid_gather": (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "rqb200_sid_prefix_workspace_bytes": (c_size, [c_int, c_int]),
+    "rqb200_sid_prefix_build": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_size, c_vp]),
+    "rqb200_sid_prefix_check": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "rqb200_sid_beam_select": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
+                                       c_vp, c_vp, c_vp]),
     "rqb200_bf16_image_bytes": (c_size, [c_int, c_int]),
     "rqb200_f32_to_bf16_image": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "rqb200_gemm_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp]),

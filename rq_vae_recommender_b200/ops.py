@@ -543,6 +543,73 @@ def sid_dedup_rank(ids: torch.Tensor, K: int):
     return rank, dict(max_rank=stats[0], n_unique=stats[1], entropy=entropy[0])
 
 
+class SidPrefixIndex:
+    """Valid-prefix index of a corpus id table [N, C] (modules/model.py:169-182): one bitmap per prefix length, built once per
+    corpus by rqb200_sid_prefix_build.  ``check`` is the reference's `_check_valid_prefix`; ``beam_select`` one selection step of
+    its constrained beam search (model.py:340-376)."""
+
+    def __init__(self, cached_ids: torch.Tensor, codebook_size: int):
+        _need_cuda(cached_ids)
+        lib = _lib.load()
+        ids = cached_ids.to(torch.int64).contiguous()
+        self.N, self.C = ids.shape
+        self.K = int(codebook_size)
+        self.device = ids.device
+        nbytes = lib.rqb200_sid_prefix_workspace_bytes(self.C, self.K)
+        if nbytes == 0:
+            raise _lib.Rqb200Error(f"prefix index: key space {self.K}^{self.C} exceeds the bitmap limit (2^33 bits)")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.rqb200_sid_prefix_build(_p(ids), self.N, self.C, self.K, _p(self.ws), nbytes, _stream()),
+                       "sid_prefix_build")
+        _count(1)
+
+    def check(self, prefix: torch.Tensor) -> torch.Tensor:
+        """bool [P]: does some corpus row start with prefix[p] ([P, l], l <= C)."""
+        _need_cuda(prefix)
+        lib = _lib.load()
+        if prefix.dtype != torch.int64:
+            prefix = prefix.to(torch.int64)
+        if prefix.stride(-1) != 1:
+            prefix = prefix.contiguous()
+        P, l = prefix.shape
+        if l > self.C:
+            raise ValueError(f"prefix length {l} exceeds the id tuple length {self.C}")
+        valid = torch.empty(P, dtype=torch.bool, device=prefix.device)
+        with torch.cuda.device(prefix.device):
+            _lib.check(lib.rqb200_sid_prefix_check(_p(prefix), prefix.stride(0), P, l, self.C, self.K, _p(self.ws), _p(valid),
+                                                   _stream()), "sid_prefix_check")
+        _count(1)
+        return valid
+
+    def beam_select(self, samples: torch.Tensor, samp_log_p: torch.Tensor, generated: Optional[torch.Tensor],
+                    log_probas: Optional[torch.Tensor], k: int):
+        """samples / samp_log_p [B * kp, nc] (kp = 1 on the first level), generated [B, kp, h] or None, log_probas [B, kp] or None
+        -> (generated [B, k, h + 1], log_probas [B, k], parent_global [B * k]) exactly as model.py:353-388 computes them."""
+        _need_cuda(samples, samp_log_p)
+        lib = _lib.load()
+        if generated is None:
+            B, kp, h = samples.shape[0], 1, 0
+        else:
+            B, kp, h = generated.shape
+            generated = generated.to(torch.int64).contiguous()
+        nc = samples.shape[-1]
+        samples = samples.to(torch.int64).reshape(B * kp, nc).contiguous()
+        samp_log_p = samp_log_p.to(torch.float32).reshape(B * kp, nc).contiguous()
+        if log_probas is not None:
+            log_probas = log_probas.to(torch.float32).reshape(B, kp).contiguous()
+        dev = samples.device
+        out_g = torch.empty((B, k, h + 1), dtype=torch.int64, device=dev)
+        out_p = torch.empty((B, k), dtype=torch.float32, device=dev)
+        out_parent = torch.empty((B * k,), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqb200_sid_beam_select(_p(samples), _p(samp_log_p), _p(generated), _p(log_probas), B, kp, nc, h, k,
+                                                  self.C, self.K, _p(self.ws), _p(out_g), _p(out_p), _p(out_parent), _stream()),
+                       "sid_beam_select")
+        _count(1)
+        return out_g, out_p, out_parent
+
+
 def sid_gather(cached_ids: torch.Tensor, item_ids: torch.Tensor, seq_mask: Optional[torch.Tensor] = None,
                want_token_type: bool = True):
     """cached_ids[item_ids] -> [B, S*C] with -1 under the padding mask, and token_type_ids (semids.py:112-146), one launch."""

@@ -312,7 +312,88 @@ def g_tokenizer():
          shape=np.array([N, Din, D, hidden[0], K, L]))
 
 
+def g_beam():
+    """Constrained beam search, data side (modules/model.py:169-182, :300-391).  The UNMODIFIED `generate` and
+    `_check_valid_prefix` of EncoderDecoderRetrievalModel run on a stand-in `self`: the transformer passes return seeded random
+    activations (the decoder step itself is not part of this fixture), everything the search does with them -- sampling, prefix
+    validity against the corpus, scoring, sort, top-k, parent gather, cache reorder index -- is the reference's code.  Recorded
+    per hierarchy level: the logits, the sampled tokens, the validity mask, the beams entering the level, the reorder index;
+    and the final beams and log-probabilities."""
+    import importlib
+    import types as _types
+    stub = sys.modules.pop("accelerate", None)              # transformers probes the real package: the harness stub has no spec
+    try:
+        M = importlib.import_module("modules.model")
+    finally:
+        if stub is not None:
+            sys.modules["accelerate"] = stub
+    B, k, H, K, N, d = 6, 5, 4, 16, 300, 8
+    rs = np.random.RandomState(900)
+    corpus = rs.randint(0, K, size=(N, H)).astype(np.int64)
+    corpus[:, 0] = rs.randint(0, 6, size=N)                   # a few first-level ids never occur: invalid candidates exist
+    rec = dict(logits=[], prefix=[], valid=[], future=[], parent=[])
+
+    class FakeCache:
+        def __init__(self, *a, **kw):
+            pass
+        def reorder_cache(self, idx):
+            rec["parent"].append(idx.clone())
+    class Head(torch.nn.Module):
+        def __init__(self, seed):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.w = torch.randn(d, K, generator=g) * 1.5
+        def forward(self, x):
+            out = x @ self.w
+            rec["logits"].append(out.clone())
+            return out
+    fake = _types.SimpleNamespace(top_k_for_generation=k, num_embeddings_per_hierarchy=K, num_hierarchies=H,
+                                  codebooks=t(corpus), decoder_mlp=[Head(910 + h) for h in range(H)])
+    gen = torch.Generator().manual_seed(901)
+    def encoder_forward_pass(attention_mask, input_ids, user_id=None):
+        return torch.randn(B, 3, d, generator=gen), torch.ones(B, 3, dtype=torch.bool)
+    def decoder_forward_pass(future_ids, encoder_output, attention_mask_for_encoder, use_cache, past_key_values):
+        rows = encoder_output.shape[0]
+        rec["future"].append(None if future_ids is None else future_ids.clone())
+        return torch.randn(rows, 1, d, generator=gen), past_key_values
+    def check(prefix, batch_size=100000):
+        out = M.EncoderDecoderRetrievalModel._check_valid_prefix(fake, prefix, batch_size)
+        rec["prefix"].append(prefix.clone()); rec["valid"].append(out.clone())
+        return out
+    fake.encoder_forward_pass, fake.decoder_forward_pass, fake._check_valid_prefix = encoder_forward_pass, decoder_forward_pass, check
+    orig = (M.EncoderDecoderCache, M.DynamicCache)
+    M.EncoderDecoderCache, M.DynamicCache = FakeCache, FakeCache
+    try:
+        torch.manual_seed(902)                                # torch.multinomial inside generate
+        generated, log_probas = M.EncoderDecoderRetrievalModel.generate.__wrapped__(fake, None, torch.zeros(B, 1, dtype=torch.long)) \
+            if hasattr(M.EncoderDecoderRetrievalModel.generate, "__wrapped__") else \
+            M.EncoderDecoderRetrievalModel.generate(fake, None, torch.zeros(B, 1, dtype=torch.long))
+    finally:
+        M.EncoderDecoderCache, M.DynamicCache = orig
+    out = dict(corpus=corpus, shape=np.array([B, k, H, K, N]), generated=generated.numpy(), log_probas=log_probas.numpy())
+    for h in range(H):
+        out[f"logits{h}"] = rec["logits"][h].numpy()
+        out[f"prefix{h}"] = rec["prefix"][h].numpy()
+        out[f"valid{h}"] = rec["valid"][h].numpy()
+        if h > 0:
+            out[f"future{h}"] = rec["future"][h].numpy()
+            out[f"parent{h}"] = rec["parent"][h - 1].numpy()
+    # a larger validity-only case: every prefix length, present and absent prefixes, ids outside [0, K)
+    corpus2 = rs.randint(0, 256, size=(5000, 4)).astype(np.int64)
+    corpus2[:, 3] = rs.randint(0, 3, size=5000)
+    fake2 = _types.SimpleNamespace(codebooks=t(corpus2))
+    for l in range(1, 5):
+        pres = corpus2[rs.randint(0, 5000, size=400), :l]
+        absent = rs.randint(0, 256, size=(400, l)).astype(np.int64)
+        odd = pres.copy()[:20]; odd[:, -1] = np.array([-1, 256, 300, 1 << 40] * 5)
+        pf = np.concatenate([pres, absent, odd])
+        out[f"v2_prefix{l}"] = pf
+        out[f"v2_valid{l}"] = M.EncoderDecoderRetrievalModel._check_valid_prefix(fake2, t(pf)).numpy()
+    out["v2_corpus"] = corpus2.astype(np.int16)
+    save("beam", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["quantize", "rqvae_c1", "rq_ns", "beauty", "mlp", "kmeans", "gumbel", "tokenizer"]
+    which = sys.argv[1:] or ["quantize", "rqvae_c1", "rq_ns", "beauty", "mlp", "kmeans", "gumbel", "tokenizer", "beam"]
     for w in which:
         globals()["g_" + w]()

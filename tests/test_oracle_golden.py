@@ -185,3 +185,35 @@ def test_torch_cpu_port_matches_numpy_oracle_and_reference():
     ids = OT.rq_tokenize(torch.from_numpy(x), [torch.from_numpy(c) for c in cbs]).numpy()
     assert_ids_match(ids, g["eval_ids"], x, cbs)
     assert_ids_match(ids, O.rq_tokenize(x, cbs), x, cbs)
+
+
+def _beam_levels(g):
+    B, k, H, K, N = (int(v) for v in g["shape"])
+    nc = min(64, K)
+    for h in range(H):
+        logits = g[f"logits{h}"].astype(np.float64)
+        e = np.exp(logits - logits.max(axis=1, keepdims=True))
+        probas = (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
+        samples = g[f"prefix{h}"][:, -1].reshape(-1, nc)
+        samp_log_p = np.log(np.take_along_axis(probas, samples, 1))
+        yield h, samples, samp_log_p
+
+
+def test_beam_oracle_vs_reference_generate():
+    """oracle.check_valid_prefix / beam_select chained over the hierarchy levels reproduce the UNMODIFIED reference generate()
+    (tests/golden/beam.npz: per-level validity masks, beams, cache-reorder indices, final beams and log-probabilities)."""
+    g = load_golden("beam")
+    B, k, H, K, N = (int(v) for v in g["shape"])
+    corpus = g["corpus"]
+    generated, log_probas = None, None
+    for h, samples, samp_log_p in _beam_levels(g):
+        assert np.array_equal(O.check_valid_prefix(corpus, g[f"prefix{h}"]), g[f"valid{h}"])
+        if h > 0:
+            assert np.array_equal(generated.reshape(-1, h), g[f"future{h}"])          # the beams the reference fed to its decoder
+        generated, log_probas, parent = O.beam_select(corpus, samples, samp_log_p, generated, log_probas, k)
+        if h > 0:
+            assert np.array_equal(parent.reshape(-1), g[f"parent{h}"])
+    assert np.array_equal(generated, g["generated"])
+    np.testing.assert_allclose(log_probas, g["log_probas"], rtol=2e-5, atol=1e-6)
+    for l in range(1, 5):
+        assert np.array_equal(O.check_valid_prefix(g["v2_corpus"].astype(np.int64), g[f"v2_prefix{l}"]), g[f"v2_valid{l}"])

@@ -43,4 +43,9 @@ ops.MLPFunction.apply(xm, True, *ws).sum().backward()
 x, cbs = I.rq_problem(640, 64, 256, 1, seed=26)
 xt = dev(x).requires_grad_(True); ct = dev(cbs[0]).requires_grad_(True)
 e, ids, loss = ops.GumbelQuantizeFunction.apply(xt, ct, dev(I.rand(27, 640, 256)), 0.2, 0.25); (e.sum() + loss.sum()).backward()
+# prefix index + beam selection (ragged batch, out-of-range ids)
+corp = torch.randint(0, 16, (333, 3), device='cuda'); pidx = ops.SidPrefixIndex(corp, 16)
+pidx.check(torch.randint(-2, 18, (1001, 2), device='cuda'))
+g1, p1, _ = pidx.beam_select(torch.randint(0, 16, (5, 16), device='cuda'), torch.randn(5, 16, device='cuda'), None, None, 3)
+pidx.beam_select(torch.randint(0, 16, (15, 16), device='cuda'), torch.randn(15, 16, device='cuda'), g1, p1, 3)
 torch.cuda.synchronize(); print("sanitize pass done")
