@@ -20,6 +20,9 @@ own shard (items are independent: weak scaling, no data-path collective); the ti
   pipeline      (N = 1) the shipped architecture: 768-512-256-128-32 encoder (split-precision tensor-core GEMMs) + 3-level RQ at
                 D = 32, 65 536 items, index-exact precision: encoder ms, tokenise ms, id agreement with the CUDA-core SGEMM path
 
+  c4            (N = 1) BASELINE config 4 shapes, fp32 I/O: a 3-level Gumbel-softmax chain and the rotation-trick chain at
+                65 536 x 768, forward and forward + backward, device-timed, with the train-forward algorithmic bytes of SURVEY 8(d)
+
 --impl reference times that CPU port as the reference arm (the reference is pure Python/PyTorch: there is nothing
 to compile into oracle/_ref).
 """
@@ -337,6 +340,55 @@ def run_pipeline(torch, ops):
             "unique_id_tuples": int(torch.unique(ids, dim=0).shape[0])}
 
 
+def run_c4(x, cbs, torch, ops):
+    """BASELINE configs[3]: the training-mode paths at 64K x 768 (fp32 I/O; a bf16-I/O variant is not built).  Algorithmic bytes per
+    item: train forward 6 184 B, + 3 072 B of injected uniforms for Gumbel; backward 9 244 B."""
+    T, beta = 0.2, 0.25
+    xg = x.detach().clone().requires_grad_(True)
+    cg = [c.detach().clone().requires_grad_(True) for c in cbs]
+    us = [torch.rand(N_ITEMS, K, device="cuda") for _ in range(L)]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def rot_fwd():
+        return ops.RqChainFunction.apply(xg, ops.MODE_ROTATION, beta, True, *cg)
+
+    def rot_fb():
+        e, _n, _i, loss = rot_fwd()
+        (e.sum() + loss.sum()).backward()
+
+    def gum_fwd():
+        res, tot, loss = xg, 0, 0
+        for l in range(L):
+            emb, _ids, ls = ops.GumbelQuantizeFunction.apply(res, cg[l], us[l], T, beta)
+            res, tot, loss = res - emb, tot + emb, loss + ls
+        return tot, loss
+
+    def gum_fb():
+        e, loss = gum_fwd()
+        (e.sum() + loss.sum()).backward()
+
+    out = {}
+    with torch.no_grad():
+        out["rotation_fwd_ms"] = _event_ms(torch, rot_fwd, n=5, warm=2)
+        out["gumbel_fwd_ms"] = _event_ms(torch, gum_fwd, n=5, warm=2)
+    out["rotation_fwd_bwd_ms"] = _event_ms(torch, rot_fb, n=5, warm=2)
+    out["gumbel_fwd_bwd_ms"] = _event_ms(torch, gum_fb, n=5, warm=2)
+    fwd_b, noise_b = 6184.0, 4.0 * K * L
+    out["rotation_fwd_frac_of_hbm_roofline"] = N_ITEMS * fwd_b / (out["rotation_fwd_ms"] * 1e-3) / 1e9 / peak
+    out["gumbel_fwd_frac_of_hbm_roofline"] = N_ITEMS * (fwd_b + noise_b) / (out["gumbel_fwd_ms"] * 1e-3) / 1e9 / peak
+    out["gumbel_fwd_tflops_fp32_equivalent"] = 2 * 2.0 * N_ITEMS * D * K * L / (out["gumbel_fwd_ms"] * 1e-3) / 1e12
+    out["note"] = ("fp32 I/O; rotation = tensor-core tokeniser (ids) + one streaming pass over the given ids (outputs, bit-identical to the "
+                   "fused CUDA-core chain) + one backward launch; Gumbel = per level "
+                   "split-precision tensor-core GEMMs x.C^T and W.C + row kernels; compute-bound, not HBM-bound: the fractions "
+                   "say how far from the byte floor the FLOPs keep these paths")
+    return {"items": N_ITEMS, **out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -504,7 +556,8 @@ def main():
         if c3 is not None:
             out["c3"] = c3
         if world == 1:
-            for name, fn in (("c2", lambda: run_c2(x, cbs, torch, ops)), ("pipeline", lambda: run_pipeline(torch, ops))):
+            for name, fn in (("c2", lambda: run_c2(x, cbs, torch, ops)), ("pipeline", lambda: run_pipeline(torch, ops)),
+                             ("c4", lambda: run_c4(x, cbs, torch, ops))):
                 try:
                     out[name] = fn()
                 except Exception as e:        # an auxiliary record must never take the headline line down

@@ -54,6 +54,13 @@ int rqb200_rq_forward(int mode, const float* x, int64_t ldx, const float* const*
                       int L, float beta, int64_t* ids, float* embeddings, float* residuals, float* emb_sum,
                       float* emb_norms, float* loss, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same outputs from GIVEN ids (no distance computation): the streaming half of the chain.  With the ids of the
+ * tensor-core tokeniser (identical to the exact kernel's) this is how a large training-mode batch runs: tokenise + this pass
+ * instead of CUDA-core distances; outputs are bit-identical to rqb200_rq_forward's for the same ids. */
+int rqb200_rq_forward_from_ids(int mode, const float* x, int64_t ldx, const float* const* codebooks, const int64_t* ids,
+                               int B, int D, int K, int L, float beta, float* embeddings, float* residuals, float* emb_sum,
+                               float* emb_norms, float* loss, void* stream);
+
 /* Backward of the above (autograd of quantize.py:130-161 + loss.py:38-41 through the chain rqvae.py:125-132;
  * formulas SURVEY appendix A.3).  Upstream grads come with element strides so expanded / permuted torch
  * tensors need no copy: g_emb[b,d,l] = g_emb[b*ge_sB + d*ge_sD + l*ge_sL] (NULL = zero), same for g_res;

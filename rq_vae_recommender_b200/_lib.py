@@ -35,6 +35,8 @@ _SIGNATURES = {
     "rqb200_rq_workspace_bytes": (c_size, [c_int, c_int, c_int]),
     "rqb200_rq_forward": (c_int, [c_int, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    "rqb200_rq_forward_from_ids": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp]),
     "rqb200_rq_backward": (c_int, [c_int, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
                                    c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
                                    c_vp, c_vp, c_vp]),

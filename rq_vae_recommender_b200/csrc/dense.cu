@@ -207,25 +207,36 @@ __global__ void gumbel_bwd_ge_kernel(const float* g_out, int64_t go_sB, int64_t 
   gE[i] = go + 2.f * gm * (E[i] - x[(int64_t)row * ldx + d]);
 }
 
-// gdist = -W * (gW - sum_k W gW) / T  (in place over gW);  rowsum[b] = sum_k gdist ; colsum[k] += gdist (atomics)
+// gdist = -W * (gW - sum_k W gW) / T  (in place over gW);  rowsum[b] = sum_k gdist ; colsum[k] += gdist
+// Column sums: every CTA walks its rows (grid-stride) and keeps the K partial sums in shared memory, one global atomic per column
+// and CTA at the end (one atomic per ELEMENT into 256 addresses ran at 3 % of the SM throughput: profiles/r2_kernels_ncu_summary.csv)
 __global__ void gumbel_bwd_softmax_kernel(const float* w, float* gw, int B, int K, float temperature, float* rowsum,
                                           float* colsum) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= B) return;
-  const float* wr = w + (int64_t)row * K;
-  float* gr = gw + (int64_t)row * K;
-  float dot = 0.f;
-  for (int k = lane; k < K; k += 32) dot = fmaf(wr[k], gr[k], dot);
-  dot = warp_sum(dot);
-  float rs = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float gd = -(wr[k] * (gr[k] - dot) / temperature);
-    gr[k] = gd;
-    rs += gd;
-    atomicAdd(colsum + k, gd);
+  extern __shared__ float s_col[];                            // [K] (K <= GUMBEL_SMEM_K), else straight to global
+  const bool use_s = K <= 8192;
+  if (use_s)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_col[k] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+    const float* wr = w + (int64_t)row * K;
+    float* gr = gw + (int64_t)row * K;
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot = fmaf(wr[k], gr[k], dot);
+    dot = warp_sum(dot);
+    float rs = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float gd = -(wr[k] * (gr[k] - dot) / temperature);
+      gr[k] = gd;
+      rs += gd;
+      atomicAdd(use_s ? s_col + k : colsum + k, gd);
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) rowsum[row] = rs;
   }
-  rs = warp_sum(rs);
-  if (lane == 0) rowsum[row] = rs;
+  __syncthreads();
+  if (use_s)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(colsum + k, s_col[k]);
 }
 
 // gx = 2 beta gamma (x - E) + 2 x rowsum - 2 (gdist @ C)   where `acc` holds gdist @ C on entry   [B,D]
@@ -329,7 +340,9 @@ extern "C" int rqb200_gumbel_bwd_softmax(const float* weights, float* gw_inout, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   RQB_CUDA(cudaMemsetAsync(colsum, 0, (size_t)K * sizeof(float), st));
   if (B == 0) return RQB_OK;
-  gumbel_bwd_softmax_kernel<<<ROW_GRID(B), 0, st>>>(weights, gw_inout, B, K, temperature, rowsum, colsum);
+  int grid = (B + 7) / 8;
+  if (grid > 148 * 4) grid = 148 * 4;
+  gumbel_bwd_softmax_kernel<<<grid, 256, K <= 8192 ? (size_t)K * sizeof(float) : 0, st>>>(weights, gw_inout, B, K, temperature, rowsum, colsum);
   RQB_LAUNCH_CHECK();
   return RQB_OK;
 }

@@ -344,6 +344,87 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) rq_fused_kernel(RqParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward from given ids
+// The per-row epilogue of rq_fused_kernel on its own: with the ids already known (from the tensor-core tokeniser, whose ids are
+// those of the exact kernel) the embeddings / residuals / sums / norms / loss of all L levels are a streaming pass -- one warp
+// per row, the residual in shared memory, the SAME loops and reductions as above, hence bit-identical outputs.  This is what
+// makes the training-mode forward of a large batch HBM-bound instead of CUDA-core-FLOP-bound (65 536 x 768, L = 3: 5.7 ms fused).
+__global__ void rq_replay_kernel(RqParams p) {
+  extern __shared__ __align__(16) float rsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* Rrow = rsm + (size_t)warp * p.D;
+  for (int row = blockIdx.x * wpb + warp; row < p.B; row += gridDim.x * wpb) {
+    const float* xr = p.x + (int64_t)row * p.ldx;
+    for (int d = lane; d < p.D; d += 32) Rrow[d] = __ldg(xr + d);
+    __syncwarp();
+    float loss_acc = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      int64_t bi = p.ids[(int64_t)row * p.L + l];
+      if (bi < 0 || bi >= p.K) bi = 0;                        // memory-safe on a corrupt id
+      const float* __restrict__ e_ptr = p.cb[l] + bi * p.D;
+      float* emb_o = p.emb ? p.emb + ((int64_t)l * p.B + row) * p.D : nullptr;
+      float* res_o = p.resid ? p.resid + ((int64_t)l * p.B + row) * p.D : nullptr;
+      float* sum_o = p.emb_sum ? p.emb_sum + (int64_t)row * p.D : nullptr;
+      float rnorm = 0.f, enorm = 0.f, wn = 1.f, rw = 0.f, ru = 0.f, scale = 1.f, ud = 1.f, qd = 1.f;
+      if (p.mode == RQ_MODE_ROT) {                            // quantize.py:140-153, 34-50
+        float rr = 0.f, ee = 0.f;
+        for (int d = lane; d < p.D; d += 32) {
+          const float r = Rrow[d], e = __ldg(e_ptr + d);
+          rr = fmaf(r, r, rr);
+          ee = fmaf(e, e, ee);
+        }
+        rnorm = sqrtf(warp_sum(rr));
+        enorm = sqrtf(warp_sum(ee));
+        ud = rnorm + 1e-8f;
+        qd = enorm + 1e-8f;
+        float ww = 0.f;
+        for (int d = lane; d < p.D; d += 32) {
+          const float w = Rrow[d] / ud + __ldg(e_ptr + d) / qd;
+          ww = fmaf(w, w, ww);
+        }
+        wn = fmaxf(sqrtf(warp_sum(ww)), 1e-6f);
+        for (int d = lane; d < p.D; d += 32) {
+          const float r = Rrow[d];
+          const float u = r / ud, q = __ldg(e_ptr + d) / qd;
+          const float w = (u + q) / wn;
+          rw = fmaf(r, w, rw);
+          ru = fmaf(r, u, ru);
+        }
+        rw = warp_sum(rw);
+        ru = warp_sum(ru);
+        scale = enorm / (rnorm + 1e-6f);
+      }
+      float s = 0.f, nn = 0.f;
+      for (int d = lane; d < p.D; d += 32) {
+        const float r = Rrow[d], e = __ldg(e_ptr + d);
+        const float df = r - e;
+        s = fmaf(df, df, s);
+        float eo;
+        if (p.mode == RQ_MODE_EVAL) {
+          eo = e;
+        } else if (p.mode == RQ_MODE_STE) {
+          eo = r + (e - r);
+        } else {
+          const float u = r / ud, q = e / qd;
+          const float w = (u + q) / wn;
+          eo = ((r - 2.f * (rw * w)) + 2.f * (ru * q)) * scale;
+        }
+        if (res_o) res_o[d] = r;
+        if (emb_o) emb_o[d] = eo;
+        if (sum_o) sum_o[d] = (l == 0) ? eo : (sum_o[d] + eo);
+        Rrow[d] = r - eo;
+        nn = fmaf(eo, eo, nn);
+      }
+      s = warp_sum(s);
+      nn = warp_sum(nn);
+      loss_acc += s + p.beta * s;
+      if (lane == 0 && p.emb_norm) p.emb_norm[(int64_t)row * p.L + l] = sqrtf(nn);
+      __syncwarp();
+    }
+    if (lane == 0 && p.loss) p.loss[row] = loss_acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 struct RqBwdParams {
   const float* x;
@@ -630,6 +711,31 @@ extern "C" int rqb200_rq_forward(int mode, const float* x, int64_t ldx, const fl
   p.B = B; p.D = D; p.K = K; p.L = L; p.beta = beta; p.mode = mode;
   p.ids = ids; p.emb = embeddings; p.resid = residuals; p.emb_sum = emb_sum; p.emb_norm = emb_norms; p.loss = loss;
   return dispatch_fused(p, false, st);
+}
+
+extern "C" int rqb200_rq_forward_from_ids(int mode, const float* x, int64_t ldx, const float* const* codebooks,
+                                          const int64_t* ids, int B, int D, int K, int L, float beta, float* embeddings,
+                                          float* residuals, float* emb_sum, float* emb_norms, float* loss, void* stream) {
+  RQB_CHECK_ARG(mode == RQ_MODE_EVAL || mode == RQ_MODE_STE || mode == RQ_MODE_ROT, "rq_forward_from_ids: bad mode %d", mode);
+  RQB_CHECK_ARG(B >= 0 && D > 0 && K > 0 && L > 0 && L <= RQB_MAX_LEVELS && ldx >= D, "rq_forward_from_ids: bad shape");
+  if (B == 0) return RQB_OK;
+  RQB_CHECK_ARG(x && codebooks && ids, "rq_forward_from_ids: null pointer");
+  RqParams p{};
+  p.x = x; p.ldx = ldx;
+  for (int l = 0; l < L; ++l) { RQB_CHECK_ARG(codebooks[l], "rq_forward_from_ids: null codebook %d", l); p.cb[l] = codebooks[l]; }
+  p.B = B; p.D = D; p.K = K; p.L = L; p.beta = beta; p.mode = mode;
+  p.ids = const_cast<int64_t*>(ids);
+  p.emb = embeddings; p.resid = residuals; p.emb_sum = emb_sum; p.emb_norm = emb_norms; p.loss = loss;
+  int wpb = 8;
+  while (wpb > 1 && (size_t)wpb * D * sizeof(float) > 96 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * D * sizeof(float);
+  if (smem > 200 * 1024) { rqb_set_error("rq_forward_from_ids: D too large (%d)", D); return RQB_ERR_UNSUPPORTED; }
+  RQB_CUDA(cudaFuncSetAttribute(rq_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (B + wpb - 1) / wpb;
+  if (grid > 148 * 8) grid = 148 * 8;
+  rq_replay_kernel<<<grid, wpb * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  RQB_LAUNCH_CHECK();
+  return RQB_OK;
 }
 
 extern "C" int rqb200_rq_backward(int mode, const float* x, int64_t ldx, const float* const* codebooks,

@@ -121,7 +121,8 @@ def mlp(x: Tensor, normalize: bool, weights: Sequence[Tensor]) -> Tensor:
 def rq_chain_fwd(x: Tensor, mode: int, beta: float, lean: bool, codebooks: Sequence[Tensor]) -> List[Tensor]:
     """lean: [emb_sum, emb_norms, ids, loss]; else [embeddings, residuals, ids, loss] -- modules/rqvae.py:118-139"""
     ctx = _Ctx()
-    return list(ops.RqChainFunction.forward(ctx, x, mode, beta, lean, *codebooks))
+    with ops.no_operand_cache():
+        return list(ops.RqChainFunction.forward(ctx, x, mode, beta, lean, *codebooks))
 
 
 @rq_chain_fwd.register_fake

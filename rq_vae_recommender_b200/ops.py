@@ -95,6 +95,18 @@ def rq_forward(x: torch.Tensor, codebooks: Sequence[torch.Tensor], mode: int, be
     esum = torch.empty((B, D), dtype=torch.float32, device=dev) if want_sum else None
     norms = torch.empty((B, L), dtype=torch.float32, device=dev) if want_norms else None
     loss = torch.empty((B,), dtype=torch.float32, device=dev) if want_loss else None
+    if (B >= TC_MIN_ROWS and tc_padded_dim(D, K, L)
+            and (want_embeddings or want_residuals or want_sum or want_norms or want_loss)):
+        # large batch: ids from the tensor-core tokeniser (those of the exact kernel), everything else from the streaming
+        # pass over the given ids -- same outputs bit for bit, HBM-bound instead of CUDA-core-FLOP-bound
+        tids = rq_tokenize_tc(x, state=tc_state_for(cbs))
+        with torch.cuda.device(dev):
+            _lib.check(lib.rqb200_rq_forward_from_ids(mode, _p(x), x.stride(0), _ptr_array(cbs), _p(tids), B, D, K, L,
+                                                      float(beta), _p(emb), _p(res), _p(esum), _p(norms), _p(loss), _stream()),
+                       "rq_forward_from_ids")
+        _count(1)
+        out.update(ids=tids if want_ids else None, embeddings=emb, residuals=res, emb_sum=esum, emb_norms=norms, loss=loss)
+        return out
     ws_bytes = lib.rqb200_rq_workspace_bytes(D, K, L)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

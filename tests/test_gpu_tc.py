@@ -194,3 +194,42 @@ def test_tc_beauty_codebooks_zero_padded_to_64(ops):
     pad = lambda a: np.concatenate([a, np.zeros((a.shape[0], 64 - a.shape[1]), np.float32)], axis=1)
     ids, stats = run_tc(ops, pad(z), [pad(c) for c in cbs])
     assert_ids_match(ids, g["sem_ids"], z, cbs, "tc/beauty padded")
+
+
+@pytest.mark.parametrize("D,L", [(768, 3), (32, 3), (256, 4)])
+@pytest.mark.parametrize("mode_name", ["eval", "ste", "rot"])
+def test_large_batch_forward_is_tokenise_plus_replay_and_bit_identical(D, L, mode_name):
+    """From ops.TC_MIN_ROWS rows on, the training-mode forward takes its ids from the tensor-core tokeniser and computes embeddings,
+    residuals, sums, norms and the loss in a streaming pass over the given ids (rq_replay_kernel).  Every output must equal the
+    fused CUDA-core chain's bit for bit (same ids, same loops), and the backward must not notice."""
+    from rq_vae_recommender_b200 import ops
+    mode = {"eval": ops.MODE_EVAL, "ste": ops.MODE_STE, "rot": ops.MODE_ROTATION}[mode_name]
+    B = 3000
+    x, cbs = I.rq_problem(B, D, 256, L, seed=7 * D + L)
+    xd, cd = dev(x), [dev(c) for c in cbs]
+    kw = dict(want_ids=True, want_embeddings=True, want_residuals=True, want_sum=True, want_norms=True, want_loss=True)
+    calls0 = ops.TC_CALLS
+    new = ops.rq_forward(xd, cd, mode, 0.25, **kw)
+    assert ops.TC_CALLS == calls0 + 1, "the large-batch forward must go through the tensor-core tokeniser"
+    old_min, ops.TC_MIN_ROWS = ops.TC_MIN_ROWS, 1 << 62
+    try:
+        ref = ops.rq_forward(xd, cd, mode, 0.25, **kw)
+    finally:
+        ops.TC_MIN_ROWS = old_min
+    for k in ("ids", "embeddings", "residuals", "emb_sum", "emb_norms", "loss"):
+        assert torch.equal(new[k], ref[k]), f"{mode_name} D={D} L={L}: {k} differs"
+    # autograd through the new route: gradients equal the fused route's
+    def grads():
+        xt = xd.clone().requires_grad_(True)
+        ct = [c.clone().requires_grad_(True) for c in cd]
+        e, n, ids, loss = ops.RqChainFunction.apply(xt, mode, 0.25, True, *ct)
+        (e.sum() + loss.sum()).backward()
+        return [xt.grad] + [c.grad for c in ct]
+    g_new = grads()
+    ops.TC_MIN_ROWS = 1 << 62
+    try:
+        g_ref = grads()
+    finally:
+        ops.TC_MIN_ROWS = old_min
+    for a, b in zip(g_new, g_ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * b.abs().max().item())      # codebook grads: fp32 atomics, order varies run to run
