@@ -24,6 +24,15 @@ for _ in range(reps):
     cg = (torch.randn(256, 768, device="cuda") * 0.05).requires_grad_(True)
     e, gi, gl = ops.GumbelQuantizeFunction.apply(xg, cg, torch.rand(16384, 256, device="cuda"), 0.2, 0.25)
     (e.sum() + gl.sum()).backward()
+    # corpus-side kernels: dedup rank + statistics, sequence gather, prefix index + beam selection
+    ids3 = torch.randint(0, 256, (84000, 3), device="cuda")
+    rank, st = ops.sid_dedup_rank(ids3, 256)
+    table = torch.cat([ids3, rank.clamp_max(255).unsqueeze(1)], 1)
+    ops.sid_gather(table, torch.randint(0, 84000, (256, 20), device="cuda"), torch.rand(256, 20, device="cuda") > 0.2)
+    pidx = ops.SidPrefixIndex(table, 256)
+    pidx.check(table[torch.randint(0, 84000, (163840,), device="cuda")])
+    g1, p1, _ = pidx.beam_select(torch.randint(0, 256, (256, 64), device="cuda"), torch.randn(256, 64, device="cuda"), None, None, 10)
+    pidx.beam_select(torch.randint(0, 256, (2560, 64), device="cuda"), torch.randn(2560, 64, device="cuda"), g1, p1, 10)
     # small-batch SGEMM (the reference's training batch sizes)
     ops.sgemm(torch.randn(256, 768, device="cuda"), ws[0].detach(), trans_b=True, relu=True)
 torch.cuda.synchronize(); print("done")
