@@ -13,7 +13,7 @@ own shard (items are independent: weak scaling, no data-path collective); the ti
   cpu_baseline  the torch-CPU port of the reference path (oracle/rq_oracle_torch.py) on this host's cores, bounded sample
   prepare_ms    one-time cost of the frozen-codebook state (fp16 images, float64 Gram tables), outside the timed steps
   c3            (N > 1) BASELINE config 3: an 84 000-item corpus sharded over the ranks: local tokenise + all-gather of the
-                int32 id blocks + all-reduce of the [L,K] usage counts per step, checked against one GPU tokenising the whole
+                int32 id blocks + all-reduce of the [L,K] usage counts per step (eager, and replayed as ONE CUDA graph), checked against one GPU tokenising the whole
                 corpus; plus one Lloyd iteration (assign + fp64 accumulate + all-reduce + update) at 20 000 x 32 and x 768
 
   c2            (N = 1) BASELINE config 2: 12 101 x 768 items, device-timed through the module-API routing (ops.rq_tokenize_auto)
@@ -224,6 +224,42 @@ def run_c3(world, rank, cbs, torch, dist, ops, parallel):
     out = {"items": n3, "steps": steps, "ms_per_step_per_rank": per_rank, "ms_per_step": max(per_rank),
            "items_per_sec": n3 / (max(per_rank) * 1e-3),
            "timed": "local tokenise + all_gather(int32 ids) + all_reduce([L,K] usage), eager launches, NCCL"}
+    # the same step captured in ONE CUDA graph (kernel + both collectives): what a serving loop would replay.  Every rank must
+    # agree that its capture succeeded before anybody replays (a captured collective replayed by one rank only would hang).
+    ok_flag = torch.ones(1, device="cuda")
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            table_g, usage_g = step()
+    except Exception as e:                                   # capture not possible here: keep the eager record
+        ok_flag[0] = 0.0
+        out["graph_error"] = f"{type(e).__name__}: {e}"[:200]
+        graph = None
+    torch.cuda.synchronize()
+    dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+    if bool(ok_flag.item() == 1.0):
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        g_ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        per_g = [torch.zeros_like(g_ms) for _ in range(world)]
+        dist.all_gather(per_g, g_ms)
+        out["graph_ms_per_step_per_rank"] = [float(t.item()) for t in per_g]
+        out["graph_ms_per_step"] = max(out["graph_ms_per_step_per_rank"])
+        out["graph_tables_equal_eager"] = bool(torch.equal(table_g, table)) and bool(torch.equal(usage_g, usage))
     match = torch.zeros(1, device="cuda")
     if rank == 0:
         xf = torch.from_numpy(x_all).cuda()
@@ -237,6 +273,8 @@ def run_c3(world, rank, cbs, torch, dist, ops, parallel):
         torch.cuda.synchronize()
         out["single_gpu_ms"] = e0.elapsed_time(e1) / 50
         out["speedup_vs_single_gpu"] = out["single_gpu_ms"] / out["ms_per_step"]
+        if "graph_ms_per_step" in out:
+            out["graph_speedup_vs_single_gpu"] = out["single_gpu_ms"] / out["graph_ms_per_step"]
         ok = bool(torch.equal(full.to(torch.int32), table)) and bool(torch.equal(ops.sid_histogram(full, K), usage))
         match[0] = 1.0 if ok else 0.0
         del xf

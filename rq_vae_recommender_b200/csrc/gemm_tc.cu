@@ -275,12 +275,9 @@ extern "C" int rqb200_gemm_bf16(const void* a_image, const void* w_image, int M,
   p.relu = relu;
   p.out_img = reinterpret_cast<unsigned char*>(out_image);
   p.out_f32 = out_f32; p.ldo = ldo;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    RQB_CUDA(cudaGetDevice(&dev));
-    RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int dev = 0, sm_count = 0;                                 // per call: the current device may differ between calls
+  RQB_CUDA(cudaGetDevice(&dev));
+  RQB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = (size_t)GT_STAGES * 3 * GT_BLK_BYTES + sizeof(GtSmemMisc);
   RQB_CUDA(cudaFuncSetAttribute(gt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.nitems < sm_count ? p.nitems : sm_count;
