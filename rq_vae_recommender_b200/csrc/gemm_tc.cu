@@ -459,6 +459,10 @@ extern "C" int rqb200_f32_to_split_image(const float* x, int64_t ldx, int rows, 
   if (transposed) {
     unsigned char* im = reinterpret_cast<unsigned char*>(image);
     const int nkc = (K + GT_KC - 1) / GT_KC;
+    if (nkc > 65535) {                                       // grid.y of the column kernels
+      rqb_set_error("f32_to_split_image: transposed operand with K = %d > %d", K, 65535 * GT_KC);
+      return RQB_ERR_UNSUPPORTED;
+    }
     float* scales = reinterpret_cast<float*>(im + 2 * (size_t)mtiles * nkc * GT_BLK_BYTES);
     RQB_CUDA(cudaMemsetAsync(scales, 0, (size_t)mtiles * 128 * sizeof(float), st));
     gs_colmax_kernel<<<dim3((rows + 255) / 256, (K + 127) / 128), 256, 0, st>>>(x, ldx, rows, K, reinterpret_cast<unsigned int*>(scales));
