@@ -13,8 +13,9 @@
 // Why transposed (round 2; the round-1 kernel had rows on the lanes): with a row per lane every score costs ~10 instructions
 // of top-3 bookkeeping and the Gram rows are per-lane gathers (32 uncoalesced 32-byte requests per row and table; measured
 // 0.53 requests/clk/SM = the L1TEX floor of the level-1/2 scans, profiles/r2_first_call_variants.txt).  With a CODE per lane
-// a row is one warp-wide step: its Gram values are ONE coalesced 128-byte line per table, the minimum over 32 codes is ONE
-// CREDUX.MIN.F32 (result in a uniform register), the candidate set is ONE ballot.  ~14 warp instructions per 32 scores
+// a row is one warp-wide step: its Gram values are ONE coalesced 128-byte line per table, the minimum over the warp's 32 codes
+// comes from a transposed butterfly over 32 rows at once (31 SHFL + 31 FMNMX per 32 rows; one CREDUX.MIN.F32 per row was tried
+// first and measured ~16 cycles per instruction and SM), the candidate set is ONE ballot.  ~14 warp instructions per 32 scores
 // instead of ~320.  The price is a merge across the 8 warps (4 TMEM lane quarters x 2 CTAs) that hold a row's 256 codes:
 // 8 bytes per (row, warp) through shared memory / DSMEM, two mbarrier hand-offs per level.
 //
@@ -97,11 +98,6 @@ struct TxSmem {
   alignas(16) uint2 xstage[TX_XBUF][4][TX_R];         // [step parity] what this CTA's warps found for the PEER's rows: one 768-byte DSMEM bulk copy per warp and level
 };
 
-__device__ __forceinline__ float tx_redux_min(float v) {     // CREDUX.MIN.F32: the warp minimum in a uniform register
-  float r;
-  asm("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
-  return r;
-}
 // ---- cluster hand-offs WITHOUT cluster-scope fences.  `mbarrier.arrive.release.cluster` / `try_wait.acquire.cluster` compile to
 // MEMBAR.ALL.GPU + ERRBAR / CCTL.IVALL (seen in SASS; ~2 K cycles per converter half-box in the first run of this kernel).
 // Remote DATA therefore travels by st.async, which completes transaction bytes on the destination CTA's mbarrier: the
