@@ -238,3 +238,28 @@ def test_bench_reference_arm_contract():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     assert "65536x768" in d["config"]["workload"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("kw", [dict(codebook_sim_vq=True), dict(codebook_normalize=True),
+                                dict(codebook_sim_vq=True, codebook_normalize=True)])
+@pytest.mark.parametrize("mode_name", ["STE", "GUMBEL_SOFTMAX"])
+def test_forward_traces_with_projected_and_normalised_codebooks(kw, mode_name):
+    """The derived-codebook variants (sim_vq projection = an MLP op on the embedding table, row-normalised first level) also
+    export as one graph."""
+    import torch
+    import rq_vae_recommender_b200.library  # noqa: F401
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode as M
+    from rq_vae_recommender_b200.data.schemas import SeqBatch
+    m = RqVae(input_dim=64, embed_dim=16, hidden_dims=[32], codebook_size=32, codebook_kmeans_init=False,
+              codebook_mode=getattr(M, mode_name), n_layers=2, commitment_weight=0.25, n_cat_features=0, **kw)
+    m.train()
+
+    def f(x):
+        out = m(SeqBatch(None, None, None, x, None, None), 0.2)
+        return out.loss, out.p_unique_ids, out.embs_norm
+
+    gm = torch._dynamo.export(f)(torch.randn(48, 64)).graph_module
+    names = {str(n.target) for n in gm.graph.nodes if n.op == "call_function" and "rqb200" in str(n.target)}
+    assert "rqb200.mlp_fwd.default" in names and "rqb200.count_unique_id_tuples.default" in names
+    assert ("rqb200.gumbel_level_fwd.default" if mode_name == "GUMBEL_SOFTMAX" else "rqb200.rq_chain_fwd.default") in names
