@@ -403,6 +403,37 @@ def test_forward_compiles_to_one_graph_with_custom_operators(mode_name):
         assert torch.allclose(g_comp[n], g_eager[n], rtol=1e-5, atol=1e-7 * g_eager[n].abs().max().item() + 1e-12), n
 
 
+@pytest.mark.parametrize("mode_name", ["STE", "GUMBEL_SOFTMAX"])
+def test_compiled_forward_with_projected_normalised_codebooks(mode_name):
+    """sim_vq projection + row-normalised first codebook + an L2-normalising decoder input path: compiled (one graph) == eager."""
+    import rq_vae_recommender_b200.library  # noqa: F401
+    from rq_vae_recommender_b200.modules.rqvae import RqVae
+    from rq_vae_recommender_b200.modules.quantize import QuantizeForwardMode as M
+    g, x, _ = c1_inputs(4)
+    torch.manual_seed(11)
+    m = RqVae(input_dim=x.shape[1], embed_dim=16, hidden_dims=[32], codebook_size=32, codebook_kmeans_init=False,
+              codebook_mode=getattr(M, mode_name), n_layers=2, commitment_weight=BETA, n_cat_features=4,
+              codebook_sim_vq=True, codebook_normalize=True).cuda()
+    m.train()
+    batch = batch_of(dev(x))
+    torch.manual_seed(7)
+    eager = m(batch, T)
+    eager.loss.backward()
+    g_eager = _grads(m)
+    m.zero_grad(set_to_none=True)
+    compiled = torch.compile(lambda b, t: m(b, t), backend="aot_eager", fullgraph=True)
+    torch.manual_seed(7)
+    out = compiled(batch, T)
+    assert torch.allclose(out.loss, eager.loss, rtol=1e-6), (out.loss.item(), eager.loss.item())
+    out.loss.backward()
+    g_comp = _grads(m)
+    assert g_comp.keys() == g_eager.keys() and len(g_comp) > 0
+    for n in g_eager:
+        # codebook gradients are fp32 atomics (order varies run to run) and pass through the projection / normalisation backward
+        err = (g_comp[n] - g_eager[n]).abs().max().item() / (g_eager[n].abs().max().item() + 1e-30)
+        assert err <= 2e-5, (n, err)
+
+
 def test_reduce_overhead_graph_follows_weight_updates():
     """mode="reduce-overhead" (the reference's setting) replays a CUDA graph: nothing prepared on the host at capture time may go
     stale when the optimiser updates the weights in place between replays."""
