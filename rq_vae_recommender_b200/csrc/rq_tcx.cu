@@ -29,7 +29,7 @@
 //   warps 8-15    epilogue: warp (q, ch) scans codes 128c + 32q + lane for the 96 rows of CTA ch, delivers (min, candidate mask)
 //                 per row to CTA ch; then all 8 warps of a CTA finalise its own rows (merge, exact re-rank from a shared queue)
 //                 and publish the level's ids to both CTAs (the next level's Gram rows are addressed by them).
-// Measured limits, timeline and ncu: DESIGN.md 5.2, profiles/r2_*.
+// Measured limits, timeline and ncu: DESIGN.md 5.2 / 6.1, profiles/r2_tcx_*.
 #include "tc_common.cuh"
 #include <type_traits>
 
@@ -158,8 +158,8 @@ __device__ __forceinline__ float tx_transpose_sum(const float (&v)[32], int lane
   return (u0 ? d[1] : d[0]) + __shfl_xor_sync(0xffffffffu, u0 ? d[0] : d[1], 1);
 }
 // Barrier wait that does not spin: try_wait with a suspend-time hint parks the warp until the phase completes (or ~20 us pass).
-// The first run of this kernel spent 40 % of its executed instructions in try_wait / clock64 polling loops (ncu, profiles/
-// r2_tcx_ncu_v5.txt): warps that wait must not take issue slots from the four converter / eight epilogue warps that work.
+// The first run of this kernel spent 40 % of its executed instructions in try_wait / clock64 polling loops (ncu capture of
+// that build, summarised in DESIGN.md 5.2): warps that wait must not take issue slots from the four converter / eight epilogue warps that work.
 __device__ __forceinline__ bool tx_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
